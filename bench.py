@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+"""Benchmark of the render + fitness hot path (BASELINE.json metric: candidate evals/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one fused render+fitness evaluation of one population on each GPU (plus, for N > 1,
+the NCCL all-gather of the fitness vector).  Default workload is BASELINE config 3:
+256x256 px, 1,000 splats, population 1,024 per GPU, mask-weighted fitness.  One JSON line on
+stdout (rank 0); everything else goes to stderr.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "genetic-gaussian-splats_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "candidate_evals_per_sec"
+UNIT = "candidates/s"
+FLOP_PER_PAIR = 23          # SURVEY.md section 8d, counted from render.py:189-196
+FLOP_PER_PIXEL = 12         # fitness.py:16-31
+NOMINAL_FP32_TFLOPS = 74.4  # 148 SM x 128 lanes x 2 flop x 1.965 GHz (clocks.max.sm)
+
+WORKLOADS = {
+    # name: H, W, N splats, population per GPU, masked fitness
+    "c1": dict(H=128, W=128, N=100, P=32, mask=True,
+               desc="config 1: 128x128, 100 splats, population 32"),
+    "c2": dict(H=256, W=256, N=500, P=8, mask=True,
+               desc="config 2: 256x256, 500 splats, 8 batched SA neighbours"),
+    "c3": dict(H=256, W=256, N=1000, P=1024, mask=True,
+               desc="config 3: GA 256x256, 1,000 splats, population 1,024 per GPU, "
+                    "mask-weighted fitness"),
+    "c4": dict(H=512, W=512, N=4000, P=1024, mask=True,
+               desc="config 4 shard: 512x512, 4,000 splats, 1,024 candidates per GPU "
+                    "(8,192 over 8 GPUs)"),
+}
+POOL = 4  # distinct populations rotated through the timed loop
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def dist_env():
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+# --------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_id: str):
+        self.gpu_id, self.proc, self.lines = gpu_id, None, []
+
+    def _cmd(self, loop: bool):
+        cmd = ["nvidia-smi", "-i", self.gpu_id, f"--query-gpu={self.FIELDS}",
+               "--format=csv,noheader,nounits"]
+        return cmd + (["-lms", "50"] if loop else [])
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(self._cmd(True), stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception as e:  # nvidia-smi missing: report it, do not fail the bench
+            log(f"[bench] clock sampler unavailable: {e}")
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        lines = list(self.lines)
+        if not lines:
+            try:
+                lines = subprocess.run(self._cmd(False), capture_output=True, text=True,
+                                       timeout=20).stdout.strip().splitlines()
+            except Exception:
+                lines = []
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+                pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "power_w_max": float(max(pw)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ CPU (reference) arm
+
+def cpu_sample(wl, seconds: float, rank_seed: int = 0):
+    """Times the CPU oracle (the restatement of the reference's arithmetic; the reference has
+    no CPU path of its own) on a bounded sample of the workload.  Returns (cands/s, sample)."""
+    from ggs_b200 import synth
+    from oracle import oracle
+    H, W, N = wl["H"], wl["W"], wl["N"]
+    cores = oracle.threads()
+    t = synth.synthetic_target_np(H, W, 0)
+    m = synth.importance_mask_np(t) if wl["mask"] else None
+    probe = synth.new_population_np(cores, N, H, W, seed=42 + rank_seed)
+    t0 = time.perf_counter()
+    oracle.fitness(probe, t, H, W, 3.0, weight_mask=m)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    n = int(max(cores, min(wl["P"], round(seconds / dt) * cores)))
+    g = synth.new_population_np(n, N, H, W, seed=43 + rank_seed)
+    t0 = time.perf_counter()
+    oracle.fitness(g, t, H, W, 3.0, weight_mask=m)
+    dt = time.perf_counter() - t0
+    return n / dt, n, cores, dt
+
+
+def run_reference(args, wl):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return 0
+    from oracle import oracle
+    oracle.build()
+    cores = oracle.threads()
+    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_sample(wl, per_step / 4)
+    vals, n_last, t_total = [], 0, 0.0
+    for s in range(args.steps):
+        v, n, cores, dt = cpu_sample(wl, per_step, rank_seed=s)
+        vals.append(v)
+        n_last = n
+        t_total += dt
+    value = float(np.mean(vals))
+    sample = (f"{n_last} candidates of {wl['H']}x{wl['W']}/{wl['N']} splats per step, "
+              f"CPU oracle (oracle/ggs_oracle.c, OpenMP over candidates)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "H": wl["H"], "W": wl["W"], "splats": wl["N"],
+                   "population_per_gpu": wl["P"], "fitness": "mask" if wl["mask"] else "plain",
+                   "note": "the reference has no CPU path (render.py:217 asserts CUDA); this arm "
+                           "times the CPU restatement of its arithmetic on the host cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------ our arm
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    import ggs_b200
+    from ggs_b200 import synth
+
+    rank, local_rank, world = dist_env()
+    if args.gpus > 1 and world != args.gpus:
+        log(f"[bench] --gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+        return 2
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    ggs_b200.lib()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    H, W, N, P = wl["H"], wl["W"], wl["N"], wl["P"]
+    K, Wm = args.steps, args.warmup
+    t_np = synth.synthetic_target_np(H, W, 0)
+    m_np = synth.importance_mask_np(t_np) if wl["mask"] else None
+    target = torch.from_numpy(t_np).to(dev)
+    mask = None if m_np is None else torch.from_numpy(m_np).to(dev)
+
+    # Each rank owns its shard of the population (weak scaling: P candidates per GPU).  POOL
+    # distinct populations are rotated so consecutive steps never read the same genomes.
+    host_pool = [torch.from_numpy(synth.new_population_np(P, N, H, W, seed=42 + 1000 * rank + r))
+                 .pin_memory() for r in range(POOL)]
+    pool = [h.to(dev) for h in host_pool]
+    pool_bytes = sum(h.numel() * 4 for h in host_pool)
+
+    pairs = []
+    for g in pool:
+        d = ggs_b200.decode(g, H, W, 3.0, layout=ggs_b200.LAYOUT_AXES_ANGLE)
+        area = (d["x1"] - d["x0"] + 1).clamp_min(0).long() * (d["y1"] - d["y0"] + 1).clamp_min(0).long()
+        pairs.append(int(area.sum().item()))
+    flop_per_launch = [FLOP_PER_PAIR * p + FLOP_PER_PIXEL * P * H * W for p in pairs]
+
+    peaks = ggs_b200.probe_peaks()
+    log(f"[bench rank {rank}] probe: {peaks}")
+
+    all_fit = torch.empty((world * P,), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def step(i):
+        fit = ggs_b200.fitness(pool[i % POOL], target, H, W, 3.0, weight_mask=mask)
+        if world > 1:
+            dist.all_gather_into_tensor(all_fit, fit)
+            return all_fit
+        return fit
+
+    for i in range(max(Wm, 0)):
+        step(i)
+    torch.cuda.synchronize(dev)
+
+    props = torch.cuda.get_device_properties(dev)
+    sampler = ClockSampler("GPU-" + str(props.uuid) if hasattr(props, "uuid") else str(local_rank))
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ggs_b200.timing_enable(True)
+    e0.record()
+    last = None
+    for i in range(K):
+        last = step(Wm + i)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    kt = ggs_b200.timing_read()
+    ggs_b200.timing_enable(False)
+    clocks = sampler.stop()
+    assert torch.isfinite(last).all()
+
+    # ---- end to end: host buffers through the C ABI, H2D + D2H inside the timed region
+    he = ggs_b200.HostEvaluator(t_np, m_np, device=local_rank)
+    out = torch.empty((P,), dtype=torch.float32).pin_memory()
+    for i in range(min(max(Wm, 1), 3)):
+        he.fitness(host_pool[i % POOL], out=out)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        he.fitness(host_pool[(Wm + i) % POOL], out=out)
+    e2e_s = time.perf_counter() - t0
+    he.close()
+    # the host path must agree bit for bit with the device path on the same genomes
+    chk = ggs_b200.fitness(pool[(Wm + K - 1) % POOL], target, H, W, 3.0, weight_mask=mask)
+    assert torch.equal(chk.cpu(), out), "host path disagrees with device path"
+
+    t_max = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    ms_all, e2e_ms_all = float(t_max[0]), float(t_max[1])
+
+    if rank == 0:
+        value = world * P * K / (ms_all * 1e-3)
+        e2e_value = world * P * K / (e2e_ms_all * 1e-3)
+        flops_timed = sum(flop_per_launch[(Wm + i) % POOL] for i in range(K))
+        raster_s = kt["raster_ms"] * 1e-3
+        achieved = flops_timed / raster_s / 1e12 if raster_s > 0 else None
+        roofline = {
+            "bound": "fp32", "kernel": "ggs::raster_kernel", "achieved": achieved,
+            "peak": NOMINAL_FP32_TFLOPS, "unit": "TFLOP/s",
+            "frac": None if achieved is None else achieved / NOMINAL_FP32_TFLOPS,
+            "traffic": None,
+            "peak_source": "nominal 148 SM x 128 lanes x 2 x clocks.max.sm 1965 MHz; "
+                           "MEASURED_PEAKS.json has no fp32 entry (HBM and bf16 tensor only)",
+            "measured_ffma_tflops": peaks["ffma_tflops"],
+            "measured_ffma2_tflops": peaks["ffma2_tflops"],
+            "measured_mufu_ex2_gops": peaks["mufu_ex2_gops"],
+            "frac_of_measured_ffma": None if achieved is None else achieved / peaks["ffma_tflops"],
+            "algorithmic_flop_per_launch": float(np.mean(flop_per_launch)),
+            "pairs_per_candidate": float(np.mean(pairs)) / P,
+            "raster_ms_per_launch": kt["raster_ms"] / max(1, kt["evaluations"]),
+            "decode_ms_per_launch": kt["decode_ms"] / max(1, kt["evaluations"]),
+            "raster_share_of_step": kt["raster_ms"] / ms if ms > 0 else None,
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            try:
+                v, n, cores, dt = cpu_sample(wl, args.cpu_seconds)
+                cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                       "sample": f"{n} candidates of the same workload in {dt:.1f} s, CPU oracle "
+                                 f"(oracle/ggs_oracle.c, OpenMP over candidates, scalar expf)"}
+            except Exception as e:
+                log(f"[bench] cpu_baseline failed: {e}")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": Wm, "ms_per_step": ms_all / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "H": H, "W": W, "splats": N,
+                       "population_per_gpu": P, "population_total": world * P,
+                       "fitness": "mask" if wl["mask"] else "plain", "k_sigma": 3.0,
+                       "parallelism": f"population sharded over {world} GPU(s), NCCL all-gather of "
+                                      f"the fitness vector" if world > 1 else "1 GPU",
+                       "l2": f"inputs rotate over {POOL} populations ({pool_bytes / 1e6:.0f} MB "
+                             f"> 126 MB L2)" if pool_bytes > 126e6 else
+                             f"inputs rotate over {POOL} populations ({pool_bytes / 1e6:.0f} MB); "
+                             f"compute-bound, {N * 36} B of genome per candidate"},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": P * N * 9 * 4, "d2h_bytes_per_step": P * 4,
+                    "ms_per_step": e2e_ms_all / K,
+                    "api": "ggs_ctx_fitness_host (C ABI, pinned host genomes in, host fitness out)"},
+            "gpu_launches": 2 * K,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c3")
+    ap.add_argument("--population", type=int, default=None, help="override candidates per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    if args.population:
+        wl["P"] = args.population
+    if args.warmup < 3 and args.impl == "ours":
+        log("[bench] note: fewer than 3 warm-up steps requested")
+    return run_reference(args, wl) if args.impl == "reference" else run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

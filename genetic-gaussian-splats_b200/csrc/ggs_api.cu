@@ -1,0 +1,433 @@
+// extern "C" surface of libggs_b200.so (include/ggs_b200.h): argument checking, workspace
+// carving, launch sequencing and the host-buffer path.  No kernels live here.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "ggs_common.cuh"
+
+namespace ggs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return GGS_ECUDA;
+}
+
+#define GGS_CUDA(call)                                   \
+    do {                                                 \
+        cudaError_t e_ = (call);                         \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+size_t workspace_bytes(int B, int N, int H, int W)
+{
+    const size_t S = (size_t)B * (size_t)N;
+    const size_t nt = (size_t)tiles_x(W) * tiles_y(H);
+    size_t n = 0;
+    n += align_up(S * sizeof(SplatRec), 256);
+    n += align_up(S * sizeof(uint2), 256);
+    n += align_up((size_t)B * nt * sizeof(float2), 256);
+    n += align_up((size_t)B * sizeof(int), 256);
+    return n;
+}
+
+Workspace carve_workspace(void *base, int B, int N, int H, int W)
+{
+    const size_t S = (size_t)B * (size_t)N;
+    const size_t nt = (size_t)tiles_x(W) * tiles_y(H);
+    char *p = static_cast<char *>(base);
+    Workspace ws;
+    ws.rec = reinterpret_cast<float4 *>(p);
+    p += align_up(S * sizeof(SplatRec), 256);
+    ws.aabb = reinterpret_cast<uint2 *>(p);
+    p += align_up(S * sizeof(uint2), 256);
+    ws.partial = reinterpret_cast<float2 *>(p);
+    p += align_up((size_t)B * nt * sizeof(float2), 256);
+    ws.counter = reinterpret_cast<int *>(p);
+    return ws;
+}
+
+static int check_shape(int B, int N, int cols, int H, int W)
+{
+    if (B < 0 || N < 0) {
+        set_error("B and N must be non-negative (got B=%d N=%d)", B, N);
+        return GGS_EINVAL;
+    }
+    if (cols < 9) {
+        set_error("expected at least 9 genome cols (got %d)", cols);
+        return GGS_EINVAL;
+    }
+    if (H < 1 || W < 1 || H > GGS_MAX_SIDE || W > GGS_MAX_SIDE) {
+        set_error("H and W must be in [1, %d] (got H=%d W=%d)", GGS_MAX_SIDE, H, W);
+        return GGS_EINVAL;
+    }
+    return GGS_OK;
+}
+
+static int check_layout(int layout)
+{
+    if (layout != GGS_LAYOUT_AXES_ANGLE && layout != GGS_LAYOUT_CHOLESKY) {
+        set_error("unknown genome layout %d", layout);
+        return GGS_EINVAL;
+    }
+    return GGS_OK;
+}
+
+// ---- optional per-kernel event log (ggs_timing_*) ------------------------------------
+struct TimingLog {
+    static constexpr int kCap = 4096;
+    bool enabled = false;
+    int used = 0;       // evaluations logged
+    int created = 0;    // event triples created so far
+    cudaEvent_t ev[kCap][3];
+};
+static TimingLog g_timing;
+
+static cudaEvent_t *timing_slot()
+{
+    if (!g_timing.enabled || g_timing.used >= TimingLog::kCap) return nullptr;
+    if (g_timing.used == g_timing.created) {
+        for (int k = 0; k < 3; ++k)
+            if (cudaEventCreate(&g_timing.ev[g_timing.created][k]) != cudaSuccess) return nullptr;
+        ++g_timing.created;
+    }
+    return g_timing.ev[g_timing.used++];
+}
+
+// decode + raster on `stream`; the one launch sequence behind every public entry.
+static int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
+                    float k_sigma, const float bg[3], const float *d_target, const float *d_mask,
+                    int mode, float beta, float *d_fitness, float *d_images, void *d_workspace,
+                    size_t workspace_bytes_given, cudaStream_t stream)
+{
+    if (B == 0) return GGS_OK;
+    if (d_genomes == nullptr && N > 0) {
+        set_error("d_genomes is NULL");
+        return GGS_EINVAL;
+    }
+    const size_t need = workspace_bytes(B, N, H, W);
+    if (d_workspace == nullptr || workspace_bytes_given < need) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes_given);
+        return GGS_EWORKSPACE;
+    }
+    if ((reinterpret_cast<uintptr_t>(d_workspace) & 255u) != 0) {
+        set_error("workspace must be 256-byte aligned");
+        return GGS_EINVAL;
+    }
+    const Workspace ws = carve_workspace(d_workspace, B, N, H, W);
+    cudaEvent_t *ev = timing_slot();
+    if (ev) GGS_CUDA(cudaEventRecord(ev[0], stream));
+    GGS_CUDA(launch_decode(d_genomes, layout, (int64_t)B * N, cols, H, W, k_sigma, ws.rec, ws.aabb,
+                           nullptr, nullptr, ws.counter, B, stream));
+    if (ev) GGS_CUDA(cudaEventRecord(ev[1], stream));
+    GGS_CUDA(launch_raster(ws, B, N, H, W, bg, d_target, d_mask, mode, beta, d_fitness, d_images,
+                           stream));
+    if (ev) GGS_CUDA(cudaEventRecord(ev[2], stream));
+    return GGS_OK;
+}
+
+}  // namespace ggs
+
+using namespace ggs;
+
+extern "C" {
+
+int ggs_abi_version(void) { return GGS_ABI_VERSION; }
+
+const char *ggs_last_error(void) { return g_err; }
+
+int ggs_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    return n;
+}
+
+size_t ggs_workspace_bytes(int B, int N, int H, int W)
+{
+    if (B < 0 || N < 0 || H < 1 || W < 1) return 0;
+    return workspace_bytes(B, N, H, W);
+}
+
+int ggs_encode(const float *d_axes, int64_t rows, int cols, float *d_chol, void *stream)
+{
+    if (rows < 0 || cols < 9 || (rows > 0 && (d_axes == nullptr || d_chol == nullptr))) {
+        set_error("ggs_encode: bad arguments (rows=%lld cols=%d)", (long long)rows, cols);
+        return GGS_EINVAL;
+    }
+    GGS_CUDA(launch_encode(d_axes, rows, cols, d_chol, static_cast<cudaStream_t>(stream)));
+    return GGS_OK;
+}
+
+int ggs_decode(const float *d_genomes, int layout, int64_t rows, int cols, int H, int W,
+               float k_sigma, float *d_out_f, int32_t *d_out_i, void *stream)
+{
+    int rc = check_layout(layout);
+    if (rc) return rc;
+    rc = check_shape(0, 0, cols, H, W);
+    if (rc) return rc;
+    if (rows < 0 || (rows > 0 && (d_genomes == nullptr || d_out_f == nullptr || d_out_i == nullptr))) {
+        set_error("ggs_decode: bad arguments");
+        return GGS_EINVAL;
+    }
+    GGS_CUDA(launch_decode(d_genomes, layout, rows, cols, H, W, k_sigma, nullptr, nullptr, d_out_f,
+                           d_out_i, nullptr, 0, static_cast<cudaStream_t>(stream)));
+    return GGS_OK;
+}
+
+int ggs_render(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
+               float k_sigma, const float *h_background, float *d_images, void *d_workspace,
+               size_t workspace_bytes_given, void *stream)
+{
+    int rc = check_layout(layout);
+    if (rc) return rc;
+    rc = check_shape(B, N, cols, H, W);
+    if (rc) return rc;
+    if (B > 0 && d_images == nullptr) {
+        set_error("ggs_render: d_images is NULL");
+        return GGS_EINVAL;
+    }
+    const float white[3] = {1.0f, 1.0f, 1.0f};
+    const float *bg = h_background ? h_background : white;
+    return evaluate(d_genomes, layout, B, N, cols, H, W, k_sigma, bg, nullptr, nullptr,
+                    GGS_MODE_PLAIN, 1.0f, nullptr, d_images, d_workspace, workspace_bytes_given,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int ggs_fitness(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
+                float k_sigma, const float *d_target, const float *d_mask, int mode,
+                float boost_beta, float *d_fitness, float *d_images, void *d_workspace,
+                size_t workspace_bytes_given, void *stream)
+{
+    int rc = check_layout(layout);
+    if (rc) return rc;
+    rc = check_shape(B, N, cols, H, W);
+    if (rc) return rc;
+    if (mode != GGS_MODE_PLAIN && mode != GGS_MODE_MASK && mode != GGS_MODE_BOOST) {
+        set_error("unknown fitness mode %d", mode);
+        return GGS_EINVAL;
+    }
+    if (B > 0 && (d_target == nullptr || d_fitness == nullptr)) {
+        set_error("ggs_fitness: d_target / d_fitness is NULL");
+        return GGS_EINVAL;
+    }
+    if (mode != GGS_MODE_PLAIN && d_mask == nullptr) {
+        set_error("ggs_fitness: mode %d needs a weight mask", mode);
+        return GGS_EINVAL;
+    }
+    const float white[3] = {1.0f, 1.0f, 1.0f};  // render.py:209
+    return evaluate(d_genomes, layout, B, N, cols, H, W, k_sigma, white, d_target, d_mask, mode,
+                    boost_beta, d_fitness, d_images, d_workspace, workspace_bytes_given,
+                    static_cast<cudaStream_t>(stream));
+}
+
+/* ---------------------------------------------------------------------------------- */
+/* host-buffer path                                                                    */
+
+struct ggs_ctx {
+    int device = 0;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    float *d_target = nullptr;
+    float *d_mask = nullptr;
+    int H = 0, W = 0;
+    bool has_mask = false;
+    // per-stream slice buffers (grow-only)
+    float *d_genomes[2] = {nullptr, nullptr};
+    size_t genomes_cap[2] = {0, 0};
+    void *d_ws[2] = {nullptr, nullptr};
+    size_t ws_cap[2] = {0, 0};
+    float *d_fitness = nullptr;
+    size_t fitness_cap = 0;
+};
+
+static int grow(void **p, size_t *cap, size_t need)
+{
+    if (*cap >= need) return GGS_OK;
+    if (*p) GGS_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    GGS_CUDA(cudaMalloc(p, need));
+    *cap = need;
+    return GGS_OK;
+}
+
+int ggs_ctx_create(int device, ggs_ctx **out)
+{
+    if (out == nullptr) {
+        set_error("ggs_ctx_create: out is NULL");
+        return GGS_EINVAL;
+    }
+    *out = nullptr;
+    int n = 0;
+    GGS_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) {
+        set_error("ggs_ctx_create: device %d not visible (%d devices)", device, n);
+        return GGS_ENODEVICE;
+    }
+    GGS_CUDA(cudaSetDevice(device));
+    ggs_ctx *c = new (std::nothrow) ggs_ctx();
+    if (!c) {
+        set_error("out of host memory");
+        return GGS_EINVAL;
+    }
+    c->device = device;
+    for (int i = 0; i < 2; ++i) {
+        GGS_CUDA(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
+        GGS_CUDA(cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming));
+    }
+    *out = c;
+    return GGS_OK;
+}
+
+void ggs_ctx_destroy(ggs_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (int i = 0; i < 2; ++i) {
+        if (c->stream[i]) cudaStreamSynchronize(c->stream[i]);
+        if (c->d_genomes[i]) cudaFree(c->d_genomes[i]);
+        if (c->d_ws[i]) cudaFree(c->d_ws[i]);
+        if (c->done[i]) cudaEventDestroy(c->done[i]);
+        if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
+    }
+    if (c->d_target) cudaFree(c->d_target);
+    if (c->d_mask) cudaFree(c->d_mask);
+    if (c->d_fitness) cudaFree(c->d_fitness);
+    delete c;
+}
+
+int ggs_ctx_set_target(ggs_ctx *c, const float *h_target, const float *h_mask, int H, int W)
+{
+    if (!c || !h_target) {
+        set_error("ggs_ctx_set_target: NULL argument");
+        return GGS_EINVAL;
+    }
+    int rc = check_shape(0, 0, 9, H, W);
+    if (rc) return rc;
+    GGS_CUDA(cudaSetDevice(c->device));
+    for (int i = 0; i < 2; ++i) GGS_CUDA(cudaStreamSynchronize(c->stream[i]));
+    if (c->d_target) GGS_CUDA(cudaFree(c->d_target));
+    if (c->d_mask) GGS_CUDA(cudaFree(c->d_mask));
+    c->d_target = c->d_mask = nullptr;
+    const size_t P = (size_t)H * W;
+    GGS_CUDA(cudaMalloc(&c->d_target, P * 3 * sizeof(float)));
+    GGS_CUDA(cudaMemcpy(c->d_target, h_target, P * 3 * sizeof(float), cudaMemcpyHostToDevice));
+    c->has_mask = (h_mask != nullptr);
+    if (h_mask) {
+        GGS_CUDA(cudaMalloc(&c->d_mask, P * sizeof(float)));
+        GGS_CUDA(cudaMemcpy(c->d_mask, h_mask, P * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    c->H = H;
+    c->W = W;
+    return GGS_OK;
+}
+
+int ggs_ctx_fitness_host(ggs_ctx *c, const float *h_genomes, int layout, int B, int N, int cols,
+                         float k_sigma, int mode, float boost_beta, float *h_fitness)
+{
+    if (!c || c->d_target == nullptr) {
+        set_error("ggs_ctx_fitness_host: call ggs_ctx_set_target first");
+        return GGS_EINVAL;
+    }
+    int rc = check_layout(layout);
+    if (rc) return rc;
+    rc = check_shape(B, N, cols, c->H, c->W);
+    if (rc) return rc;
+    if (mode != GGS_MODE_PLAIN && !c->has_mask) {
+        set_error("ggs_ctx_fitness_host: mode %d needs a mask in ggs_ctx_set_target", mode);
+        return GGS_EINVAL;
+    }
+    if (B == 0) return GGS_OK;
+    if (!h_genomes || !h_fitness) {
+        set_error("ggs_ctx_fitness_host: NULL buffer");
+        return GGS_EINVAL;
+    }
+    GGS_CUDA(cudaSetDevice(c->device));
+
+    // Slices alternate between two streams so the H2D copy of slice k+1 overlaps the kernels
+    // of slice k.  Slice = at most a quarter of the population, at least 64 candidates.
+    const int slice = std::max(64, (B + 3) / 4);
+    const size_t row_bytes = (size_t)N * cols * sizeof(float);
+    rc = grow(reinterpret_cast<void **>(&c->d_fitness), &c->fitness_cap, (size_t)B * sizeof(float));
+    if (rc) return rc;
+    for (int i = 0; i < 2; ++i) {
+        const int sb = std::min(slice, B);
+        rc = grow(reinterpret_cast<void **>(&c->d_genomes[i]), &c->genomes_cap[i],
+                  std::max<size_t>(sb * row_bytes, 256));
+        if (rc) return rc;
+        rc = grow(&c->d_ws[i], &c->ws_cap[i], workspace_bytes(sb, N, c->H, c->W));
+        if (rc) return rc;
+    }
+    const float white[3] = {1.0f, 1.0f, 1.0f};
+    int k = 0;
+    for (int b0 = 0; b0 < B; b0 += slice, ++k) {
+        const int sb = std::min(slice, B - b0);
+        const int s = k & 1;
+        GGS_CUDA(cudaMemcpyAsync(c->d_genomes[s], h_genomes + (size_t)b0 * N * cols, sb * row_bytes,
+                                 cudaMemcpyHostToDevice, c->stream[s]));
+        rc = evaluate(c->d_genomes[s], layout, sb, N, cols, c->H, c->W, k_sigma, white, c->d_target,
+                      c->d_mask, mode, boost_beta, c->d_fitness + b0, nullptr, c->d_ws[s],
+                      c->ws_cap[s], c->stream[s]);
+        if (rc) return rc;
+    }
+    // Drain: stream 1's work must finish before the single D2H issued on stream 0.
+    GGS_CUDA(cudaEventRecord(c->done[1], c->stream[1]));
+    GGS_CUDA(cudaStreamWaitEvent(c->stream[0], c->done[1], 0));
+    GGS_CUDA(cudaMemcpyAsync(h_fitness, c->d_fitness, (size_t)B * sizeof(float),
+                             cudaMemcpyDeviceToHost, c->stream[0]));
+    GGS_CUDA(cudaStreamSynchronize(c->stream[0]));
+    return GGS_OK;
+}
+
+int ggs_timing_enable(int enable)
+{
+    g_timing.enabled = (enable != 0);
+    g_timing.used = 0;
+    return GGS_OK;
+}
+
+int ggs_timing_read(float *h_decode_ms, float *h_raster_ms, int *h_evaluations)
+{
+    double dec = 0.0, ras = 0.0;
+    for (int i = 0; i < g_timing.used; ++i) {
+        GGS_CUDA(cudaEventSynchronize(g_timing.ev[i][2]));
+        float a = 0.0f, b = 0.0f;
+        GGS_CUDA(cudaEventElapsedTime(&a, g_timing.ev[i][0], g_timing.ev[i][1]));
+        GGS_CUDA(cudaEventElapsedTime(&b, g_timing.ev[i][1], g_timing.ev[i][2]));
+        dec += a;
+        ras += b;
+    }
+    if (h_decode_ms) *h_decode_ms = (float)dec;
+    if (h_raster_ms) *h_raster_ms = (float)ras;
+    if (h_evaluations) *h_evaluations = g_timing.used;
+    g_timing.used = 0;
+    return GGS_OK;
+}
+
+int ggs_probe_peaks(float *h_out5)
+{
+    if (!h_out5) {
+        set_error("ggs_probe_peaks: NULL output");
+        return GGS_EINVAL;
+    }
+    GGS_CUDA(probe_peaks(h_out5));
+    return GGS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+// Shared definitions of the sm_100a render + fitness path.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ggs_b200.h"
+
+namespace ggs {
+
+// Raster geometry: one CTA per (candidate, 32x32 tile); one warp per 32x8 band, lane = pixel
+// column, each thread owns 8 vertically adjacent pixels.  With this mapping the AABB row test
+// is warp-uniform (no per-pixel predicate) and the AABB column test is one select per
+// (thread, splat) folded into the exponent.
+constexpr int kTileW = 32;
+constexpr int kRowsPerThread = 8;
+constexpr int kWarps = 4;
+constexpr int kTileH = kWarps * kRowsPerThread;
+constexpr int kThreads = kWarps * 32;
+constexpr int kListCap = 384;  // staged splat records per flush (48 B each)
+
+constexpr int kDecodeThreads = 256;
+constexpr int kDecodeStageMaxCols = 16;
+
+// Decoded splat record, 48 B = 3 x float4, stored [B][N] in the workspace.
+//   e(X,Y) = A*qx^2 + Bq*qx*qy + Cq*qy^2 + la,  f = 2^e  ( = exp(-quad/2) * alpha )
+// with A = -0.5*log2(e)*sxx, Bq = -log2(e)*sxy, Cq = -0.5*log2(e)*syy, la = log2(alpha).
+struct __align__(16) SplatRec {
+    float cx, cy, A, Bq;
+    float Cq, la, r, g;
+    float b;
+    int xpack;  // x0 | x1 << 16   (inclusive AABB, render.py:27-28)
+    int ypack;  // y0 | y1 << 16   (render.py:29-30)
+    int flags;
+};
+static_assert(sizeof(SplatRec) == 48, "SplatRec must be 3 float4");
+
+struct Workspace {
+    float4 *rec;      // [B*N*3]
+    uint2 *aabb;      // [B*N]   x0|x1<<16, y0|y1<<16 (int16 each)
+    float2 *partial;  // [B*ntiles] (numerator, denominator) per tile
+    int *counter;     // [B] tiles finished per candidate
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline int tiles_x(int W) { return (W + kTileW - 1) / kTileW; }
+inline int tiles_y(int H) { return (H + kTileH - 1) / kTileH; }
+
+size_t workspace_bytes(int B, int N, int H, int W);
+Workspace carve_workspace(void *base, int B, int N, int H, int W);
+
+// decode.cu
+cudaError_t launch_decode(const float *d_genomes, int layout, int64_t rows, int cols, int H, int W,
+                          float k_sigma, float4 *rec, uint2 *aabb, float *raw_f, int32_t *raw_i,
+                          int *counters, int n_counters, cudaStream_t stream);
+cudaError_t launch_encode(const float *d_axes, int64_t rows, int cols, float *d_chol,
+                          cudaStream_t stream);
+
+// raster.cu
+cudaError_t launch_raster(const Workspace &ws, int B, int N, int H, int W, const float bg[3],
+                          const float *d_target, const float *d_mask, int mode, float beta,
+                          float *d_fitness, float *d_images, cudaStream_t stream);
+
+// probe.cu
+cudaError_t probe_peaks(float *h_out5);
+
+void set_error(const char *fmt, ...);
+
+}  // namespace ggs

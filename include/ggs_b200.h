@@ -1,0 +1,159 @@
+/*
+ * ggs_b200.h -- C ABI of the B200-native render + fitness hot path of
+ * genetic-gaussian-splats (libggs_b200.so, built from
+ * genetic-gaussian-splats_b200/csrc/ for sm_100a).
+ *
+ * This header is the drop-in boundary: plain pointers and sizes, no torch types.
+ * The reference is pure Python and has no FFI of its own; each entry point below
+ * names the reference function it replaces (citations into /root/reference).  The
+ * Python binding a maintainer adds (ctypes) is shown in INTEGRATION.md and shipped in
+ * genetic-gaussian-splats_b200/ggs_b200/native.py.
+ *
+ * Conventions
+ *   - all tensors are dense row-major float32 unless stated otherwise;
+ *   - "d_" pointers are device pointers on the current CUDA device, "h_" pointers are
+ *     host pointers (pinned memory makes the copies asynchronous, pageable is accepted);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *     device-pointer entries only enqueue work: they never synchronise or allocate;
+ *   - every function returns GGS_OK (0) or a negative GGS_E* code; ggs_last_error()
+ *     returns a thread-local message for the last failure;
+ *   - inputs are never written; outputs are fully overwritten.
+ *
+ * Genome layouts (one row per splat, `cols` >= 9 floats per row, extra columns ignored)
+ *   axes-angle : x, y, log sigma_x, log sigma_y, theta, r, g, b, alpha   (population.py:27-43)
+ *   Cholesky   : x, y, log l11,     log l22,     l21,   r, g, b, alpha   (encode.py:35-57)
+ *   x, y in [0,1] (fraction of W-1, H-1); r, g, b, alpha in [0,255].
+ */
+#ifndef GGS_B200_H
+#define GGS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GGS_ABI_VERSION 1
+
+#define GGS_OK 0
+#define GGS_EINVAL (-1)    /* bad argument (shape, null pointer, mode)          */
+#define GGS_ECUDA (-2)     /* a CUDA runtime call or kernel launch failed       */
+#define GGS_EWORKSPACE (-3) /* workspace too small; see ggs_workspace_bytes()    */
+#define GGS_ENODEVICE (-4) /* no sm_100 device visible                          */
+
+#define GGS_LAYOUT_AXES_ANGLE 0
+#define GGS_LAYOUT_CHOLESKY 1
+
+/* fitness.py:18-31 */
+#define GGS_MODE_PLAIN 0 /* weight_mask is None: mean over (H,W,3) of d^2                    */
+#define GGS_MODE_MASK 1  /* sum(d^2 * w) / (sum_{H,W} w + 1e-12)   (denominator not x3)       */
+#define GGS_MODE_BOOST 2 /* boost_only: mean(d^2 * wb) / (mean(wb) + 1e-12), wb=1+beta*clamp(w)*/
+
+/* Largest image side the packed int16 AABB supports. */
+#define GGS_MAX_SIDE 32768
+
+int ggs_abi_version(void);
+const char *ggs_last_error(void);
+
+/* Number of CUDA devices visible to the library, or a negative error. */
+int ggs_device_count(void);
+
+/*
+ * Device scratch needed by ggs_render / ggs_fitness for a batch of B candidates of N
+ * splats on an H x W image: decoded splat records, packed AABBs, per-tile partial sums
+ * and per-candidate completion counters.  The caller owns the buffer (e.g. a torch
+ * uint8 tensor) and may reuse it across calls on the same stream.
+ */
+size_t ggs_workspace_bytes(int B, int N, int H, int W);
+
+/*
+ * genome_to_renderer_batched (modules/encode.py:63-79, via :28-59 and :5-24).
+ * d_axes: rows x cols (cols >= 9)  ->  d_chol: rows x 9.  Colours/alpha clamped to
+ * [0,255].  Same fp32 operation order as the reference (no FMA contraction).
+ */
+int ggs_encode(const float *d_axes, int64_t rows, int cols, float *d_chol, void *stream);
+
+/*
+ * _preprocess_genome (modules/render.py:9-47), for tests and tools.
+ * d_genomes: rows x cols in `layout`; outputs in the reference's naming:
+ *   d_out_f: [9][rows] = cx, cy, sxx, sxy, syy, rc, gc, bc, a
+ *   d_out_i: [4][rows] = x0, x1, y0, y1   (int32, inclusive AABB)
+ */
+int ggs_decode(const float *d_genomes, int layout, int64_t rows, int cols, int H, int W,
+               float k_sigma, float *d_out_f, int32_t *d_out_i, void *stream);
+
+/*
+ * render_splats_rgb_triton (modules/render.py:204-252).
+ * d_genomes: [B][N][cols] in `layout` (the reference entry takes Cholesky layout);
+ * h_background: 3 floats on the host (reference default 1,1,1);
+ * d_images: [B][H][W][3] float32, clamped to [0,1].
+ */
+int ggs_render(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
+               float k_sigma, const float *h_background, float *d_images, void *d_workspace,
+               size_t workspace_bytes, void *stream);
+
+/*
+ * fitness_many (modules/fitness.py:8-31): encode + decode + render + masked squared
+ * error fused; candidate images never touch HBM unless d_images is given.
+ * d_genomes: [B][N][cols] in `layout` (the reference passes axes-angle);
+ * d_target: [H][W][3] in [0,1]; d_mask: [H][W] or NULL (required unless GGS_MODE_PLAIN);
+ * d_fitness: [B] (lower is better); d_images: [B][H][W][3] or NULL.
+ * Background is white as in the reference (render.py:209).  The per-candidate
+ * reduction order is fixed, so results are bit-reproducible run to run and
+ * independent of how a population is split into calls.
+ */
+int ggs_fitness(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
+                float k_sigma, const float *d_target, const float *d_mask, int mode,
+                float boost_beta, float *d_fitness, float *d_images, void *d_workspace,
+                size_t workspace_bytes, void *stream);
+
+/* ---- host-buffer path (fitness_population, modules/fitness.py:35-48) ------------- */
+
+typedef struct ggs_ctx ggs_ctx;
+
+/* Creates a context on `device`: two streams, grow-only device buffers. */
+int ggs_ctx_create(int device, ggs_ctx **out);
+void ggs_ctx_destroy(ggs_ctx *ctx);
+
+/*
+ * One-time upload of the target [H][W][3] and optional weight mask [H][W]; both stay
+ * resident on the device for all later ggs_ctx_fitness_host calls.
+ */
+int ggs_ctx_set_target(ggs_ctx *ctx, const float *h_target, const float *h_mask, int H, int W);
+
+/*
+ * fitness_population (modules/fitness.py:35-48) on host buffers: copies the genomes
+ * host->device in slices that overlap with the kernels of the previous slice, runs the
+ * fused evaluation, copies the B fitness values back and returns when h_fitness is
+ * valid (the counterpart of the reference's `.cpu().tolist()`).
+ * h_genomes: [B][N][cols] in `layout`; mode/boost_beta as in ggs_fitness (the mask given
+ * to ggs_ctx_set_target is used).
+ */
+int ggs_ctx_fitness_host(ggs_ctx *ctx, const float *h_genomes, int layout, int B, int N,
+                         int cols, float k_sigma, int mode, float boost_beta, float *h_fitness);
+
+/* ---- hardware probes used by bench.py for the roofline denominators -------------- */
+
+/*
+ * Measures on the current device, with CUDA events: out[0] = FFMA TFLOP/s (scalar fp32
+ * FMA, 2 flop each), out[1] = FFMA2 TFLOP/s (packed fma.rn.f32x2), out[2] = MUFU.EX2
+ * Gop/s, out[3] = SM count, out[4] = SM clock (MHz) reported by the device attributes.
+ */
+int ggs_probe_peaks(float *h_out5);
+
+/*
+ * Per-kernel timing for bench.py's roofline.  While enabled, every evaluation
+ * (ggs_render / ggs_fitness / ggs_ctx_fitness_host) records CUDA events on the caller's
+ * stream around its decode launch and around its raster launch (at most 4096 evaluations
+ * are kept).  ggs_timing_read waits for the recorded events, returns the summed decode and
+ * raster kernel times in milliseconds and the number of evaluations, and clears the log.
+ * Not thread-safe; meant for a single benchmarking thread.
+ */
+int ggs_timing_enable(int enable);
+int ggs_timing_read(float *h_decode_ms, float *h_raster_ms, int *h_evaluations);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GGS_B200_H */

@@ -1,0 +1,117 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol (no compute
+calls without a GPU), the host logic of the drop-in `modules` package, and the synthetic
+input generators."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ggs_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ggs_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    import ggs_b200
+    from ggs_b200 import native
+    L = ggs_b200.lib()
+    names = declared_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/ggs_b200.h but not exported"
+        assert n in native.SIGNATURES, f"{n} has no ctypes signature in native.py"
+    assert L.ggs_abi_version() == native.ABI_VERSION
+
+
+def test_workspace_size_is_monotone_and_nonzero():
+    import ggs_b200
+    L = ggs_b200.lib()
+    a = L.ggs_workspace_bytes(1, 1, 8, 8)
+    b = L.ggs_workspace_bytes(1024, 1000, 256, 256)
+    c = L.ggs_workspace_bytes(8192, 4000, 512, 512)
+    assert 0 < a < b < c
+    # records (48 B) + packed AABBs (8 B) dominate: about 56 B per splat
+    assert 56 * 1024 * 1000 <= b <= 60 * 1024 * 1000
+    assert L.ggs_workspace_bytes(-1, 1, 8, 8) == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from ggs_b200 import native
+    monkeypatch.setattr(native, "_lib", None)
+    monkeypatch.setattr(native, "LIB_PATH", "/nonexistent/libggs_b200.so")
+    with pytest.raises(native.GgsError, match="no CPU fallback"):
+        native.lib()
+
+
+def test_render_entry_keeps_the_reference_asserts():
+    from modules.render import _DEV, render_splats_rgb_triton
+    assert _DEV == "cuda"
+    g = torch.zeros((1, 2, 9))
+    with pytest.raises(AssertionError, match="CUDA device"):
+        render_splats_rgb_triton(g, 8, 8, device="cpu")
+    with pytest.raises(AssertionError, match="genomes must be"):
+        render_splats_rgb_triton(torch.zeros(9), 8, 8)
+    with pytest.raises(AssertionError, match="at least 9"):
+        render_splats_rgb_triton(torch.zeros((1, 2, 8)), 8, 8)
+
+
+def test_entry_signatures_match_the_reference():
+    import inspect
+    from modules.fitness import fitness_many, fitness_population
+    from modules.render import render_splats_rgb_triton
+    assert list(inspect.signature(render_splats_rgb_triton).parameters) == [
+        "genomes", "H", "W", "k_sigma", "device", "background", "tile", "num_warps",
+        "num_stages", "use_fp16_canvas"]
+    assert list(inspect.signature(fitness_many).parameters) == [
+        "pop_batch", "target", "H", "W", "k_sigma", "device", "tile", "weight_mask",
+        "boost_only", "boost_beta"]
+    assert list(inspect.signature(fitness_population).parameters) == [
+        "population", "target", "H", "W", "k_sigma", "device", "tile", "chunk", "weight_mask",
+        "boost_only"]
+    sig = inspect.signature(render_splats_rgb_triton)
+    assert sig.parameters["tile"].default == 64 and sig.parameters["k_sigma"].default == 3.0
+    assert inspect.signature(fitness_many).parameters["tile"].default == 32
+
+
+def test_mode_selection():
+    from ggs_b200 import MODE_BOOST, MODE_MASK, MODE_PLAIN, mode_of
+    assert mode_of(None, False) == MODE_PLAIN and mode_of(None, True) == MODE_PLAIN
+    assert mode_of(object(), False) == MODE_MASK and mode_of(object(), True) == MODE_BOOST
+
+
+def test_synthetic_population_follows_new_population():
+    from ggs_b200 import synth
+    g = synth.new_population_np(16, 500, 256, 192, seed=42)
+    assert g.shape == (16, 500, 9) and g.dtype == np.float32
+    assert g[..., 0:2].min() >= 0 and g[..., 0:2].max() <= 1
+    sig = np.exp(g[..., 2:4])
+    assert sig.min() >= 3.0 - 1e-4 and sig.max() <= 25.6 + 1e-3      # [3 px, 0.1*max(H,W)]
+    assert abs(sig[..., 0].mean() - (3 + 0.4 * 22.6)) < 0.5          # Beta mean 0.4
+    assert abs(sig[..., 1].mean() - (3 + 0.6 * 22.6)) < 0.5          # Beta mean 0.6
+    assert np.abs(g[..., 4]).max() <= np.pi + 1e-6
+    assert g[..., 8].min() >= 180 and g[..., 5:9].max() <= 255
+    assert np.array_equal(g, synth.new_population_np(16, 500, 256, 192, seed=42))
+
+
+def test_work_statistics_match_the_survey():
+    # 128x128, 100 splats -> 2.32e5 in-AABB pairs per candidate
+    from ggs_b200 import synth
+    from oracle import oracle
+    g = synth.new_population_np(32, 100, 128, 128, seed=42)
+    d = oracle.decode(oracle.encode(g), 128, 128)
+    pairs = synth.count_pairs(d["x0"], d["x1"], d["y0"], d["y1"]) / 32
+    assert 2.0e5 < pairs < 2.6e5
+
+
+def test_mask_matches_reference_formula_on_fixture(golden):
+    # the goldens carry the reference's own mask for their synthetic target
+    from ggs_b200 import synth
+    m = synth.importance_mask_np(golden["target"], strength=0.7)
+    np.testing.assert_allclose(m, golden["mask"], atol=1e-6)

@@ -1,0 +1,370 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden fixtures made from
+the reference and against the CPU oracle.  Run on the B200 box: pytest -m gpu.
+
+Tolerances are the north star's: image <= 1e-4 absolute, fitness <= 1e-5 relative,
+identical ranking; integer AABBs bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+IMG_TOL = 1e-4
+FIT_RTOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ggs():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ggs_b200
+    ggs_b200.lib()  # raises if libggs_b200.so is missing: no silent fallback
+    return ggs_b200
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def ulp_diff(a, b):
+    a = np.asarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.asarray(b, np.float32).view(np.int32).astype(np.int64)
+    a = np.where(a < 0, -(a & 0x7FFFFFFF), a)
+    b = np.where(b < 0, -(b & 0x7FFFFFFF), b)
+    return np.abs(a - b)
+
+
+def aabb_mismatch_mask(dec_a, dec_b):
+    """[...] bool: splats whose integer AABB differs between two decodes."""
+    bad = np.zeros(np.asarray(dec_a["x0"]).shape, dtype=bool)
+    for k in ("x0", "x1", "y0", "y1"):
+        bad |= np.asarray(dec_a[k]) != np.asarray(dec_b[k])
+    return bad
+
+
+def explained_pixels(dec_a, dec_b, bad, H, W):
+    """Pixels covered by the union of both AABBs of every mismatching splat: the only
+    places where an image may legitimately differ by more than the tolerance."""
+    B = bad.shape[0]
+    ok = np.zeros((B, H, W), dtype=bool)
+    for b, n in zip(*np.nonzero(bad)):
+        x0 = min(dec_a["x0"][b, n], dec_b["x0"][b, n])
+        x1 = max(dec_a["x1"][b, n], dec_b["x1"][b, n])
+        y0 = min(dec_a["y0"][b, n], dec_b["y0"][b, n])
+        y1 = max(dec_a["y1"][b, n], dec_b["y1"][b, n])
+        ok[b, y0:y1 + 1, x0:x1 + 1] = True
+    return ok
+
+
+def to_np(d):
+    return {k: v.cpu().numpy() for k, v in d.items()}
+
+
+# ----------------------------------------------------------------------------- goldens
+
+def test_encode_vs_reference(ggs, golden):
+    got = ggs.encode(cuda(golden["axes"])).cpu().numpy()
+    ref = golden["chol"]
+    for col in (0, 1, 5, 6, 7, 8):
+        assert np.array_equal(got[..., col], ref[..., col])
+    for col in (2, 3, 4):
+        np.testing.assert_allclose(got[..., col], ref[..., col], rtol=2e-6, atol=1e-6)
+
+
+def test_decode_aabb_bit_exact_vs_reference(ggs, golden):
+    H, W, k = int(golden["H"]), int(golden["W"]), float(golden["k_sigma"])
+    got = to_np(ggs.decode(cuda(golden["chol"]), H, W, k, layout=ggs.LAYOUT_CHOLESKY))
+    for key in ("x0", "x1", "y0", "y1"):
+        assert np.array_equal(got[key], golden["dec_" + key]), key
+    for key in ("cx", "cy", "sxx", "sxy", "syy", "rc", "gc", "bc", "a"):
+        assert ulp_diff(got[key], golden["dec_" + key]).max() <= 4, key
+
+
+def test_decode_from_axes_matches_reference_aabb(ggs, golden):
+    H, W, k = int(golden["H"]), int(golden["W"]), float(golden["k_sigma"])
+    got = to_np(ggs.decode(cuda(golden["axes"]), H, W, k, layout=ggs.LAYOUT_AXES_ANGLE))
+    ref = {key: golden["dec_" + key] for key in ("x0", "x1", "y0", "y1")}
+    assert int(aabb_mismatch_mask(got, ref).sum()) == 0
+
+
+def test_render_vs_reference_kernel(ggs, golden):
+    H, W, k = int(golden["H"]), int(golden["W"]), float(golden["k_sigma"])
+    img = ggs.render(cuda(golden["chol"]), H, W, k).cpu().numpy()
+    assert img.shape == golden["images"].shape and img.dtype == np.float32
+    assert np.abs(img - golden["images"]).max() <= IMG_TOL
+
+
+def test_fitness_three_modes_vs_reference(ggs, golden):
+    H, W, k = int(golden["H"]), int(golden["W"]), float(golden["k_sigma"])
+    a, t, m = cuda(golden["axes"]), cuda(golden["target"]), cuda(golden["mask"])
+    plain = ggs.fitness(a, t, H, W, k).cpu().numpy()
+    masked = ggs.fitness(a, t, H, W, k, weight_mask=m).cpu().numpy()
+    boost = ggs.fitness(a, t, H, W, k, weight_mask=m, boost_only=True).cpu().numpy()
+    np.testing.assert_allclose(plain, golden["fit_plain"], rtol=FIT_RTOL)
+    np.testing.assert_allclose(masked, golden["fit_mask"], rtol=FIT_RTOL)
+    np.testing.assert_allclose(boost, golden["fit_boost"], rtol=FIT_RTOL)
+    assert np.array_equal(np.argsort(masked, kind="stable"),
+                          np.argsort(golden["fit_mask"], kind="stable"))
+
+
+def test_fused_images_equal_render_entry(ggs, golden):
+    H, W, k = int(golden["H"]), int(golden["W"]), float(golden["k_sigma"])
+    a, t = cuda(golden["axes"]), cuda(golden["target"])
+    fit, img = ggs.fitness(a, t, H, W, k, want_images=True)
+    assert np.abs(img.cpu().numpy() - golden["images"]).max() <= IMG_TOL
+    fit2 = ggs.fitness(a, t, H, W, k)
+    assert torch.equal(fit, fit2)  # image output does not perturb the reduction
+
+
+# ------------------------------------------------------------------- oracle, larger sizes
+
+CASES = [
+    # (B, N, H, W, seed, late)
+    (8, 100, 128, 128, 42, False),     # BASELINE config 1 shape
+    (2, 500, 256, 256, 43, False),     # config 2 shape (SA), B=2
+    (3, 1000, 256, 256, 44, False),    # config 3 shape, 3 candidates
+    (2, 700, 200, 136, 45, True),      # ragged, late-run distribution
+    (1, 1500, 64, 96, 46, False),      # many splats per tile: several list flushes
+]
+
+
+@pytest.mark.parametrize("B,N,H,W,seed,late", CASES)
+def test_against_oracle(ggs, B, N, H, W, seed, late):
+    from ggs_b200 import synth
+    g = (synth.late_population_np if late else synth.new_population_np)(B, N, H, W, seed)
+    t = synth.synthetic_target_np(H, W, seed)
+    m = synth.importance_mask_np(t)
+
+    # decode: integer AABBs equal to the oracle's; mismatches (a transcendental differing in
+    # its last ulp exactly at an integer boundary) are counted, never hidden.
+    dec_gpu = to_np(ggs.decode(cuda(g), H, W, 3.0, layout=ggs.LAYOUT_AXES_ANGLE))
+    dec_cpu = oracle.decode(oracle.encode(g), H, W, 3.0)
+    bad = aabb_mismatch_mask(dec_gpu, dec_cpu)
+    n_bad = int(bad.sum())
+    print(f"AABB mismatches: {n_bad} of {B * N} splats")
+    assert n_bad <= max(1, (B * N) // 2000)
+
+    fit_cpu, img_cpu = oracle.fitness(g, t, H, W, 3.0, weight_mask=m, return_images=True)
+    fit_gpu, img_gpu = ggs.fitness(cuda(g), cuda(t), H, W, 3.0, weight_mask=cuda(m),
+                                   want_images=True)
+    img_gpu, fit_gpu = img_gpu.cpu().numpy(), fit_gpu.cpu().numpy()
+    err = np.abs(img_gpu - img_cpu).max(axis=-1)
+    allowed = explained_pixels(dec_gpu, dec_cpu, bad, H, W)
+    assert (err[~allowed] <= IMG_TOL).all(), float(err[~allowed].max())
+    if n_bad == 0:
+        np.testing.assert_allclose(fit_gpu, fit_cpu, rtol=FIT_RTOL)
+        assert np.array_equal(np.argsort(fit_gpu, kind="stable"),
+                              np.argsort(fit_cpu, kind="stable"))
+    else:
+        np.testing.assert_allclose(fit_gpu, fit_cpu, rtol=1e-3)
+
+    for kw in ({}, {"weight_mask": m, "boost_only": True}):
+        f_cpu = oracle.fitness(g, t, H, W, 3.0, **kw)
+        kw_gpu = {k2: (cuda(v) if isinstance(v, np.ndarray) else v) for k2, v in kw.items()}
+        f_gpu = ggs.fitness(cuda(g), cuda(t), H, W, 3.0, **kw_gpu).cpu().numpy()
+        np.testing.assert_allclose(f_gpu, f_cpu, rtol=FIT_RTOL if n_bad == 0 else 1e-3)
+
+
+# --------------------------------------------------------------------------- edge cases
+
+def test_degenerate_shapes(ggs):
+    from ggs_b200 import synth
+    for (B, N, H, W) in [(1, 1, 8, 8), (1, 1, 1, 1), (2, 3, 33, 65), (1, 5, 7, 300), (3, 2, 300, 5)]:
+        g = synth.new_population_np(B, N, H, W, seed=B + N + H)
+        t = synth.synthetic_target_np(H, W, 1)
+        f_cpu, i_cpu = oracle.fitness(g, t, H, W, 3.0, return_images=True)
+        f_gpu, i_gpu = ggs.fitness(cuda(g), cuda(t), H, W, 3.0, want_images=True)
+        assert np.abs(i_gpu.cpu().numpy() - i_cpu).max() <= IMG_TOL, (B, N, H, W)
+        np.testing.assert_allclose(f_gpu.cpu().numpy(), f_cpu, rtol=FIT_RTOL)
+
+
+def test_zero_splats_is_background(ggs):
+    H, W = 40, 24
+    g = torch.zeros((2, 0, 9), device="cuda")
+    img = ggs.render(g, H, W, 3.0, background=(0.25, 0.5, 0.75))
+    assert torch.equal(img[..., 0], torch.full((2, H, W), 0.25, device="cuda"))
+    assert torch.equal(img[..., 2], torch.full((2, H, W), 0.75, device="cuda"))
+    t = torch.rand((H, W, 3), device="cuda")
+    f = ggs.fitness(g, t, H, W, 3.0)
+    ref = ((1.0 - t.double()) ** 2).mean()
+    np.testing.assert_allclose(f.cpu().numpy(), np.full(2, float(ref)), rtol=FIT_RTOL)
+
+
+def test_background_colour_and_extra_columns(ggs):
+    from ggs_b200 import synth
+    H, W = 48, 80
+    g = synth.new_population_np(2, 40, H, W, seed=3)
+    chol = oracle.encode(g)
+    chol11 = np.concatenate([chol, np.full((2, 40, 2), 7.0, np.float32)], axis=-1)
+    bg = (0.1, 0.2, 0.3)
+    ref = oracle.render(chol, H, W, 2.0, background=bg)
+    got = ggs.render(cuda(chol11), H, W, 2.0, background=bg).cpu().numpy()
+    assert np.abs(got - ref).max() <= IMG_TOL
+
+
+def test_alpha_zero_and_appended_invisible_splats_are_exact_noops(ggs):
+    from ggs_b200 import synth
+    H, W = 96, 96
+    g = synth.new_population_np(4, 120, H, W, seed=9)
+    t = cuda(synth.synthetic_target_np(H, W, 2))
+    f0 = ggs.fitness(cuda(g), t, H, W, 3.0)
+    ghost = synth.new_population_np(4, 30, H, W, seed=10)
+    ghost[..., 8] = 0.0
+    g2 = np.concatenate([g[:, :60], ghost, g[:, 60:]], axis=1)
+    f1 = ggs.fitness(cuda(g2), t, H, W, 3.0)
+    assert torch.equal(f0, f1)
+
+
+def test_order_matters_and_is_genome_order(ggs):
+    # "over" compositing is not commutative: reversing the genome changes the image, and the
+    # GPU agrees with the oracle on both orders.
+    from ggs_b200 import synth
+    H, W = 64, 64
+    g = synth.new_population_np(1, 50, H, W, seed=21)
+    chol = oracle.encode(g)
+    rev = np.ascontiguousarray(chol[:, ::-1])
+    a = ggs.render(cuda(chol), H, W, 3.0).cpu().numpy()
+    b = ggs.render(cuda(rev), H, W, 3.0).cpu().numpy()
+    assert np.abs(a - b).max() > 1e-2
+    assert np.abs(a - oracle.render(chol, H, W, 3.0)).max() <= IMG_TOL
+    assert np.abs(b - oracle.render(rev, H, W, 3.0)).max() <= IMG_TOL
+
+
+def test_deterministic_and_split_invariant(ggs):
+    from ggs_b200 import synth
+    B, N, H, W = 37, 300, 160, 128
+    g = cuda(synth.new_population_np(B, N, H, W, seed=5))
+    t = cuda(synth.synthetic_target_np(H, W, 5))
+    m = cuda(synth.importance_mask_np(synth.synthetic_target_np(H, W, 5)))
+    f1 = ggs.fitness(g, t, H, W, 3.0, weight_mask=m)
+    f2 = ggs.fitness(g, t, H, W, 3.0, weight_mask=m)
+    assert torch.equal(f1, f2)
+    parts = torch.cat([ggs.fitness(g[:10], t, H, W, 3.0, weight_mask=m),
+                       ggs.fitness(g[10:], t, H, W, 3.0, weight_mask=m)])
+    assert torch.equal(f1, parts)
+    perm = torch.randperm(B, device="cuda")
+    assert torch.equal(ggs.fitness(g[perm].contiguous(), t, H, W, 3.0, weight_mask=m), f1[perm])
+
+
+def test_perfect_candidate_scores_zero(ggs):
+    from ggs_b200 import synth
+    H, W = 128, 96
+    g = cuda(synth.new_population_np(3, 80, H, W, seed=8))
+    _, img = ggs.fitness(g, torch.zeros((H, W, 3), device="cuda"), H, W, 3.0, want_images=True)
+    f = ggs.fitness(g, img[1].contiguous(), H, W, 3.0).cpu().numpy()
+    assert f[1] == 0.0 and f[0] > 0 and f[2] > 0
+
+
+def test_host_path_equals_device_path(ggs):
+    from ggs_b200 import synth
+    B, N, H, W = 300, 64, 96, 128
+    g = synth.new_population_np(B, N, H, W, seed=12)
+    t = synth.synthetic_target_np(H, W, 12)
+    m = synth.importance_mask_np(t)
+    dev = ggs.fitness(cuda(g), cuda(t), H, W, 3.0, weight_mask=cuda(m)).cpu().numpy()
+    he = ggs.HostEvaluator(t, m)
+    host = he.fitness(g)
+    assert np.array_equal(host, dev)
+    pinned = torch.from_numpy(g).pin_memory()
+    assert np.array_equal(he.fitness(pinned), dev)
+    plain = he.fitness(g, use_mask=False)
+    np.testing.assert_array_equal(plain, ggs.fitness(cuda(g), cuda(t), H, W, 3.0).cpu().numpy())
+    he.close()
+
+
+# ------------------------------------------------------------------ the modules/ drop-in
+
+def test_modules_entry_points(ggs, golden):
+    from modules.encode import genome_to_renderer, genome_to_renderer_batched
+    from modules.fitness import fitness_many, fitness_population
+    from modules.render import render_splats_rgb_triton
+    H, W, k = int(golden["H"]), int(golden["W"]), float(golden["k_sigma"])
+    axes = cuda(golden["axes"])
+    t, m = cuda(golden["target"]), cuda(golden["mask"])
+    pop = [axes[b] for b in range(axes.shape[0])]
+
+    G9 = genome_to_renderer_batched(axes)
+    assert G9.shape == golden["chol"].shape
+    img = render_splats_rgb_triton(G9, H, W, k_sigma=k, device="cuda", tile=32)
+    assert np.abs(img.cpu().numpy() - golden["images"]).max() <= IMG_TOL
+    one = render_splats_rgb_triton(genome_to_renderer(axes[0]), H, W, k_sigma=k, device="cuda")
+    assert one.shape == (1, H, W, 3)  # 2-D input keeps B = 1 (render.py:220-221)
+    assert torch.equal(one[0], img[0])
+
+    fm = fitness_many(pop, t, H, W, k, "cuda", tile=32, weight_mask=m)
+    np.testing.assert_allclose(fm.cpu().numpy(), golden["fit_mask"], rtol=FIT_RTOL)
+    fp = fitness_population(pop, t, H, W, k, "cuda", tile=32, chunk=None, weight_mask=m)
+    assert isinstance(fp, list) and all(isinstance(v, float) for v in fp)
+    assert fp == fm.cpu().tolist()
+    fc = fitness_population(pop, t, H, W, k, "cuda", tile=32, chunk=1, weight_mask=m)
+    assert fc == fp
+    fb = fitness_population(pop, t, H, W, k, "cuda", weight_mask=m, boost_only=True)
+    np.testing.assert_allclose(fb, golden["fit_boost"], rtol=FIT_RTOL)
+
+
+def test_prewarm_call_shape(ggs):
+    # utils.py:73-82: [1,1,9] genome, 8x8 image, tile=32 (> image)
+    from modules.render import render_splats_rgb_triton
+    import math
+    dummy = torch.tensor([[[0.5, 0.5, math.log(2.0), math.log(2.0), 0.0, 128.0, 128.0, 128.0,
+                            255.0]]], device="cuda")
+    out = render_splats_rgb_triton(dummy, 8, 8, k_sigma=3.0, device="cuda", tile=32)
+    ref = oracle.render(dummy.cpu().numpy(), 8, 8, 3.0)
+    assert np.abs(out.cpu().numpy() - ref).max() <= IMG_TOL
+
+
+# ------------------------------------------------------------------------ C ABI errors
+
+def test_c_abi_error_codes(ggs):
+    import ctypes
+    L = ggs.lib()
+    g = torch.zeros((1, 4, 9), device="cuda")
+    img = torch.zeros((1, 16, 16, 3), device="cuda")
+    ws = torch.zeros(1 << 16, dtype=torch.uint8, device="cuda")
+    bg = (ctypes.c_float * 3)(1, 1, 1)
+    rc = L.ggs_render(g.data_ptr(), 1, 1, 4, 8, 16, 16, 3.0, bg, img.data_ptr(), ws.data_ptr(),
+                      ws.numel(), None)
+    assert rc == -1 and b"9 genome cols" in L.ggs_last_error()       # GGS_EINVAL
+    rc = L.ggs_render(g.data_ptr(), 1, 1, 4, 9, 16, 16, 3.0, bg, img.data_ptr(), ws.data_ptr(),
+                      16, None)
+    assert rc == -3                                                   # GGS_EWORKSPACE
+    rc = L.ggs_fitness(g.data_ptr(), 0, 1, 4, 9, 16, 16, 3.0, img.data_ptr(), None, 1, 1.0,
+                       img.data_ptr(), None, ws.data_ptr(), ws.numel(), None)
+    assert rc == -1 and b"mask" in L.ggs_last_error()
+    rc = L.ggs_render(g.data_ptr(), 7, 1, 4, 9, 16, 16, 3.0, bg, img.data_ptr(), ws.data_ptr(),
+                      ws.numel(), None)
+    assert rc == -1
+    torch.cuda.synchronize()
+
+
+# ----------------------------------------------------- BASELINE full size: property tests
+
+def test_full_size_config3_properties(ggs):
+    """256x256, 1,000 splats, population 1,024, masked fitness (BASELINE config 3): the oracle
+    checks a sample of candidates; size-independent properties cover the whole batch."""
+    from ggs_b200 import synth
+    B, N, H, W = 1024, 1000, 256, 256
+    g_np = synth.new_population_np(B, N, H, W, seed=42)
+    t_np = synth.synthetic_target_np(H, W, 0)
+    m_np = synth.importance_mask_np(t_np)
+    g, t, m = cuda(g_np), cuda(t_np), cuda(m_np)
+
+    f = ggs.fitness(g, t, H, W, 3.0, weight_mask=m)
+    assert torch.isfinite(f).all() and (f > 0).all()
+    assert torch.equal(f, ggs.fitness(g, t, H, W, 3.0, weight_mask=m))          # idempotent
+    perm = torch.randperm(B, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    assert torch.equal(ggs.fitness(g[perm].contiguous(), t, H, W, 3.0, weight_mask=m), f[perm])
+    halves = torch.cat([ggs.fitness(g[:400], t, H, W, 3.0, weight_mask=m),
+                        ggs.fitness(g[400:], t, H, W, 3.0, weight_mask=m)])
+    assert torch.equal(halves, f)                                                # shard-invariant
+
+    sample = [0, 1, 511, 1023]
+    f_cpu = oracle.fitness(g_np[sample], t_np, H, W, 3.0, weight_mask=m_np)
+    np.testing.assert_allclose(f.cpu().numpy()[sample], f_cpu, rtol=FIT_RTOL)
+
+    # checksum of checksums: mean fitness of the batch equals the mean of the per-half means
+    tot = f.double().mean().item()
+    parts = 0.5 * (f[:512].double().mean().item() + f[512:].double().mean().item())
+    assert abs(tot - parts) <= 1e-12 * max(1.0, abs(tot))
