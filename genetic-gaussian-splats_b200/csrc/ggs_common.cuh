@@ -31,7 +31,7 @@ struct __align__(16) SplatRec {
     float b;
     int xpack;  // x0 | x1 << 16   (inclusive AABB, render.py:27-28)
     int ypack;  // y0 | y1 << 16   (render.py:29-30)
-    int flags;
+    float h;    // 2^(8*Cq) for the column recurrence, or -1: steep splat, exact path only
 };
 static_assert(sizeof(SplatRec) == 48, "SplatRec must be 3 float4");
 

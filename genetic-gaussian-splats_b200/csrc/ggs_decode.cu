@@ -77,6 +77,7 @@ __device__ __forceinline__ Chol load_chol(const float *g)
 
 struct Decoded {
     float cx, cy, sxx, sxy, syy, rc, gc, bc, a;
+    float hx, hy;  // k-sigma half extents (render.py:24-25)
     int x0, x1, y0, y1;
 };
 
@@ -109,6 +110,8 @@ __device__ __forceinline__ Decoded decode_chol(const Chol &g, int H, int W, floa
     d.a = __fdiv_rn(clamp_nan(g.a, 0.0f, 255.0f), 255.0f);                    // render.py:43
     d.cx = cx;
     d.cy = cy;
+    d.hx = hx;
+    d.hy = hy;
     return d;
 }
 
@@ -191,7 +194,13 @@ decode_kernel(const float *__restrict__ genomes, int cols, int64_t rows, int H, 
         r.b = d.bc;
         r.xpack = (d.x0 & 0xffff) | (d.x1 << 16);
         r.ypack = (d.y0 & 0xffff) | (d.y1 << 16);
-        r.flags = 0;
+        // Column recurrence of the raster (f(i+2) = f(i)*g(i), g(i+2) = g(i)*h): h = 2^(8*Cq).
+        // It is used only while the exponent moves by < 64 across a thread's 8-row strip
+        // anywhere a lane of the tile can sit (|qy| <= hy+1, |qx| <= hx+32); otherwise the
+        // splat is marked steep (h = -1) and takes the exact per-pixel path.
+        const float swing = fabsf(r.Cq) * (14.0f * (d.hy + 1.0f) + 49.0f) +
+                            7.0f * fabsf(r.Bq) * (d.hx + 32.0f);
+        r.h = (swing < 64.0f) ? exp2f(8.0f * r.Cq) : -1.0f;  // NaN swing compares false -> steep
         const float4 *rv = reinterpret_cast<const float4 *>(&r);
         rec[row * 3 + 0] = rv[0];
         rec[row * 3 + 1] = rv[1];

@@ -14,7 +14,8 @@
 // With that mapping
 //   * the AABB row test is warp-uniform: rows outside [y0,y1] are skipped by uniform branches,
 //   * the AABB column test is one select per (thread, splat) that sets the exponent to -inf,
-//   * per pixel the work is FADD + 2 FFMA (exponent, Horner in qy) + MUFU.EX2 + 3 x (FADD+FFMA).
+//   * the falloff along a thread's pixel column follows a multiplicative recurrence, and the
+//     blends run as packed FADD2/FFMA2 on row pairs (see composite_list).
 // Colours stay in registers from the first splat to the fitness reduction; images are written
 // only when asked for.  Per-tile partial sums are combined in a fixed order by the last CTA of
 // each candidate, so fitness is bit-reproducible.
@@ -32,21 +33,64 @@ __device__ __forceinline__ float ex2_approx(float x)
 
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2: one issue slot, two lanes of work) ----
+typedef unsigned long long f2_t;
+
+__device__ __forceinline__ f2_t pack2(float lo, float hi)
+{
+    f2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f2_t bcast2(float v) { return pack2(v, v); }
+__device__ __forceinline__ void unpack2(f2_t v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c)
+{
+    f2_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b)
+{
+    f2_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2_t sub2(f2_t a, f2_t b)
+{
+    f2_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// Pixel state of one thread: 8 vertically adjacent pixels as 4 packed row pairs (2k, 2k+1).
 struct Pixels {
-    float r[kRowsPerThread], g[kRowsPerThread], b[kRowsPerThread];
+    f2_t r[kRowsPerThread / 2], g[kRowsPerThread / 2], b[kRowsPerThread / 2];
 };
 
-// Blend splat `s` of the staged list into this thread's 8 pixels (render.py:175-196).
-#define GGS_PIXEL(i)                                             \
-    {                                                            \
-        const float qy = dy + (float)(i);                        \
-        const float e = fmaf(fmaf(Cq, qy, t1), qy, t0);          \
-        const float f = ex2_approx(e);                           \
-        px.r[i] = fmaf(f, cr - px.r[i], px.r[i]);                \
-        px.g[i] = fmaf(f, cg - px.g[i], px.g[i]);                \
-        px.b[i] = fmaf(f, cb - px.b[i], px.b[i]);                \
+// Exact per-pixel blend (render.py:189-196): exponent by Horner in qy, one MUFU.EX2 per pixel.
+#define GGS_BLEND1(cr_, cg_, cb_, i)                          \
+    {                                                         \
+        const float qy = dy + (float)(i);                     \
+        const float e = fmaf(fmaf(Cq, qy, t1), qy, t0);       \
+        const float f = ex2_approx(e);                        \
+        cr_ = fmaf(f, cr - cr_, cr_);                         \
+        cg_ = fmaf(f, cg - cg_, cg_);                         \
+        cb_ = fmaf(f, cb - cb_, cb_);                         \
     }
 
+// Blend the staged list into this thread's pixels, in list (= genome) order.
+//
+// Fast path (splat covers all 8 rows of the band, exponent varies gently): the Gaussian along
+// the thread's pixel column is the exponential of a quadratic, so with stride-2 steps
+//     f(i+2) = f(i) * g(i),   g(i+2) = g(i) * h,   h = 2^(8*Cq)
+// the 8 falloffs come from 4 MUFU.EX2 (f0, f1, g0, g1) and packed multiplies, and the three
+// colour blends are FADD2 + FFMA2 on row pairs: 8 issue slots per 2 pixels instead of 20.
+// Slow path (partial band, or a "steep" splat whose exponent changes too fast for the
+// recurrence to stay accurate): the exact per-pixel form, rows selected by uniform branches.
 __device__ __forceinline__ void composite_list(const float4 *__restrict__ list, int cnt, int X,
                                                float Xf, int Yb, float Ybf, Pixels &px)
 {
@@ -67,13 +111,43 @@ __device__ __forceinline__ void composite_list(const float4 *__restrict__ list, 
         t0 = in_x ? t0 : -INFINITY;                       // outside [x0,x1]: f = 2^-inf = 0
         const float dy = Ybf - q0.y;
         const float Cq = q1.x, cr = q1.z, cg = q1.w, cb = q2.x;
-        if (lo == 0 && hi == kRowsPerThread - 1) {
+        const float h = q2.w;                             // 2^(8*Cq), or < 0 for a steep splat
+        if (lo == 0 && hi == kRowsPerThread - 1 && h >= 0.0f) {
+            const f2_t QY = pack2(dy, dy + 1.0f);
+            const f2_t E = fma2(fma2(bcast2(Cq), QY, bcast2(t1)), QY, bcast2(t0));
+            const float c4 = 4.0f * Cq;
+            const f2_t D = fma2(bcast2(c4), QY, bcast2(fmaf(2.0f, t1, c4)));  // e(i+2) - e(i)
+            float e0, e1, d0, d1;
+            unpack2(E, e0, e1);
+            unpack2(D, d0, d1);
+            f2_t F = pack2(ex2_approx(e0), ex2_approx(e1));
+            f2_t G = pack2(ex2_approx(d0), ex2_approx(d1));
+            const f2_t H2 = bcast2(h), R2 = bcast2(cr), G2 = bcast2(cg), B2 = bcast2(cb);
 #pragma unroll
-            for (int i = 0; i < kRowsPerThread; ++i) GGS_PIXEL(i)
+            for (int k = 0; k < kRowsPerThread / 2; ++k) {
+                px.r[k] = fma2(F, sub2(R2, px.r[k]), px.r[k]);
+                px.g[k] = fma2(F, sub2(G2, px.g[k]), px.g[k]);
+                px.b[k] = fma2(F, sub2(B2, px.b[k]), px.b[k]);
+                if (k + 1 < kRowsPerThread / 2) {
+                    F = mul2(F, G);
+                    G = mul2(G, H2);
+                }
+            }
         } else {
 #pragma unroll
-            for (int i = 0; i < kRowsPerThread; ++i)
-                if (i >= lo && i <= hi) GGS_PIXEL(i)
+            for (int k = 0; k < kRowsPerThread / 2; ++k) {
+                if (2 * k + 1 >= lo && 2 * k <= hi) {
+                    float r0, r1, g0, g1, b0, b1;
+                    unpack2(px.r[k], r0, r1);
+                    unpack2(px.g[k], g0, g1);
+                    unpack2(px.b[k], b0, b1);
+                    if (2 * k >= lo) GGS_BLEND1(r0, g0, b0, 2 * k)
+                    if (2 * k + 1 <= hi) GGS_BLEND1(r1, g1, b1, 2 * k + 1)
+                    px.r[k] = pack2(r0, r1);
+                    px.g[k] = pack2(g0, g1);
+                    px.b[k] = pack2(b0, b1);
+                }
+            }
         }
     }
 }
@@ -101,10 +175,10 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
 
     Pixels px;
 #pragma unroll
-    for (int i = 0; i < kRowsPerThread; ++i) {
-        px.r[i] = bg_r;  // render.py:236-237
-        px.g[i] = bg_g;
-        px.b[i] = bg_b;
+    for (int k = 0; k < kRowsPerThread / 2; ++k) {
+        px.r[k] = bcast2(bg_r);  // render.py:236-237
+        px.g[k] = bcast2(bg_g);
+        px.b[k] = bcast2(bg_b);
     }
 
     const float4 *recb = rec + (int64_t)b * N * 3;
@@ -152,8 +226,12 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
 #pragma unroll
     for (int i = 0; i < kRowsPerThread; ++i) {
         const int Y = Yb + i;
+        float pr[2], pg[2], pb[2];
+        unpack2(px.r[i >> 1], pr[0], pr[1]);
+        unpack2(px.g[i >> 1], pg[0], pg[1]);
+        unpack2(px.b[i >> 1], pb[0], pb[1]);
         if (X < W && Y < H) {
-            const float cr = clamp01(px.r[i]), cg = clamp01(px.g[i]), cb = clamp01(px.b[i]);
+            const float cr = clamp01(pr[i & 1]), cg = clamp01(pg[i & 1]), cb = clamp01(pb[i & 1]);
             const int64_t p = (int64_t)Y * W + X;
             if (images != nullptr) {
                 float *o = images + ((int64_t)b * H * W + p) * 3;

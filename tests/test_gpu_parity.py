@@ -78,8 +78,12 @@ def test_decode_aabb_bit_exact_vs_reference(ggs, golden):
     got = to_np(ggs.decode(cuda(golden["chol"]), H, W, k, layout=ggs.LAYOUT_CHOLESKY))
     for key in ("x0", "x1", "y0", "y1"):
         assert np.array_equal(got[key], golden["dec_" + key]), key
-    for key in ("cx", "cy", "sxx", "sxy", "syy", "rc", "gc", "bc", "a"):
-        assert ulp_diff(got[key], golden["dec_" + key]).max() <= 4, key
+    for key in ("cx", "cy", "rc", "gc", "bc", "a"):
+        assert ulp_diff(got[key], golden["dec_" + key]).max() == 0, key
+    # the conic goes through exp (libdevice here, SLEEF in the CPU-generated goldens) and
+    # three more roundings: a few ulp, i.e. < 2e-6 relative
+    for key in ("sxx", "sxy", "syy"):
+        assert ulp_diff(got[key], golden["dec_" + key]).max() <= 16, key
 
 
 def test_decode_from_axes_matches_reference_aabb(ggs, golden):
