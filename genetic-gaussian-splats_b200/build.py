@@ -26,7 +26,9 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path
 # per-file extra flags: the decode must not contract mul+add (bit-exact AABB, SURVEY finding 4)
 SOURCES = {
     "ggs_decode.cu": ["-fmad=false"],
-    "ggs_raster.cu": [],
+    # ptxas -O3 renames the packed (64-bit) pixel accumulators out of place and pays ~20
+    # MOV/IMAD.MOV per splat to move them back; -O1 keeps FFMA2/FADD2 in place (checked in SASS)
+    "ggs_raster.cu": ["-Xptxas", "-O1"],
     "ggs_probe.cu": [],
     "ggs_api.cu": [],
 }

@@ -17,7 +17,7 @@ constexpr int kRowsPerThread = 8;
 constexpr int kWarps = 4;
 constexpr int kTileH = kWarps * kRowsPerThread;
 constexpr int kThreads = kWarps * 32;
-constexpr int kListCap = 384;  // staged splat records per flush (48 B each)
+constexpr int kListCap = 512;  // staged splat records per flush (48 B each)
 
 constexpr int kDecodeThreads = 256;
 constexpr int kDecodeStageMaxCols = 16;

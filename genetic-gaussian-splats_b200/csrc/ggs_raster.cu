@@ -6,16 +6,26 @@
 //   canvas fill / final clamp     modules/render.py:236-237, :252
 //   squared error + reductions    modules/fitness.py:16-31
 //
-// One CTA = one (candidate, 32x32 tile).  The CTA streams the candidate's packed AABBs in
-// genome order, 128 per round; a ballot/popcount prefix compacts the splats that touch the tile
-// *in order* into a shared-memory list of 48-byte records (no global sort, no host sync), and
-// whenever the list fills (or the genome ends) the four warps composite it.  Warp w owns the
-// 32x8 band of rows [8w, 8w+8): lane = pixel column, 8 vertically adjacent pixels per thread.
-// With that mapping
-//   * the AABB row test is warp-uniform: rows outside [y0,y1] are skipped by uniform branches,
-//   * the AABB column test is one select per (thread, splat) that sets the exponent to -inf,
-//   * the falloff along a thread's pixel column follows a multiplicative recurrence, and the
-//     blends run as packed FADD2/FFMA2 on row pairs (see composite_list).
+// One CTA = one (candidate, 32x32 tile).  The CTA streams the candidate's packed AABBs, 256 per
+// round; a ballot/popcount prefix compacts the splats that touch the tile *in order* into a
+// shared-memory list of 48-byte records (no global sort, no host sync), and whenever the list
+// fills (or the genome ends) the four warps composite it.  Warp w owns the 32x8 band of rows
+// [8w, 8w+8): lane = pixel column, 8 vertically adjacent pixels per thread.  With that mapping
+//   * the AABB row test is warp-uniform: the thread that stages a record precomputes, per band,
+//     which rows it covers (one byte per warp), so a warp classifies a splat with one PRMT;
+//   * the AABB column test is a per-tile lane mask precomputed the same way: one LOP3 + one
+//     select per (thread, splat) sets the exponent to -inf outside [x0, x1];
+//   * the falloff along a thread's pixel column follows a multiplicative recurrence and the
+//     blends run as packed FMUL2/FFMA2/FADD2 on row pairs (see composite_list).
+//
+// Compositing order.  The reference paints splats in genome order with the "over" operator
+// C <- (1-f) C + f col (render.py:194-196).  The same image is
+//     C = sum_n  f_n col_n  prod_{m>n} (1 - f_m)   +   bg prod_m (1 - f_m),
+// which this kernel evaluates front to back: it walks the genome from the LAST splat to the
+// first, keeping per pixel the accumulated colour and the transmittance T = prod (1 - f_m).
+// That form needs 5 packed operations per row pair instead of 6 and is algebraically identical;
+// parity with the reference is checked to 1e-4 absolute on every pixel (tests/).
+//
 // Colours stay in registers from the first splat to the fitness reduction; images are written
 // only when asked for.  Per-tile partial sums are combined in a fixed order by the last CTA of
 // each candidate, so fitness is bit-reproducible.
@@ -23,6 +33,10 @@
 
 namespace ggs {
 namespace {
+
+constexpr int kPairs = kRowsPerThread / 2;
+constexpr int kScanPerThread = 2;
+constexpr int kScanChunk = kThreads * kScanPerThread;  // records examined per round
 
 __device__ __forceinline__ float ex2_approx(float x)
 {
@@ -59,93 +73,134 @@ __device__ __forceinline__ f2_t mul2(f2_t a, f2_t b)
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-__device__ __forceinline__ f2_t sub2(f2_t a, f2_t b)
+__device__ __forceinline__ f2_t add2(f2_t a, f2_t b)
 {
     f2_t d;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// In-place forms: the "+l" constraint pins accumulator and result to the same register pair,
+// which keeps ptxas from shuffling the pixel state through temporaries.
+__device__ __forceinline__ void fma2_acc(f2_t &c, f2_t a, f2_t b)  // c += a*b
+{
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ void sub2_acc(f2_t &c, f2_t a)  // c -= a
+{
+    asm("sub.rn.f32x2 %0, %0, %1;" : "+l"(c) : "l"(a));
+}
+__device__ __forceinline__ void mul2_acc(f2_t &c, f2_t a)  // c *= a
+{
+    asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(c) : "l"(a));
+}
 
-// Pixel state of one thread: 8 vertically adjacent pixels as 4 packed row pairs (2k, 2k+1).
+// Pixel state of one thread: 8 vertically adjacent pixels as 4 packed row pairs (2k, 2k+1):
+// accumulated colour (premultiplied, front to back) and transmittance.
 struct Pixels {
-    f2_t r[kRowsPerThread / 2], g[kRowsPerThread / 2], b[kRowsPerThread / 2];
+    f2_t r[kPairs], g[kPairs], b[kPairs], t[kPairs];
 };
 
-// Exact per-pixel blend (render.py:189-196): exponent by Horner in qy, one MUFU.EX2 per pixel.
-#define GGS_BLEND1(cr_, cg_, cb_, i)                          \
-    {                                                         \
-        const float qy = dy + (float)(i);                     \
-        const float e = fmaf(fmaf(Cq, qy, t1), qy, t0);       \
-        const float f = ex2_approx(e);                        \
-        cr_ = fmaf(f, cr - cr_, cr_);                         \
-        cg_ = fmaf(f, cg - cg_, cg_);                         \
-        cb_ = fmaf(f, cb - cb_, cb_);                         \
+// Staged record (shared memory, 3 x float4), specialised for the tile by the staging thread:
+//   q0 = cx, cy, A, Bq      q1 = Cq, la, r, g      q2 = b, lane mask, row code, h
+// lane mask: bit l set iff column X0+l lies in [x0, x1].
+// row code : byte w describes band w: 0x0f = not touched, else lo | hi << 4 (rows lo..hi of the
+//            band are inside [y0, y1]) with bit 3 set for a steep splat; 0x70 = all 8 rows of a
+//            gentle splat, the only value that takes the recurrence path.
+constexpr unsigned kBandMiss = 0x0fu;
+constexpr unsigned kBandFull = 0x70u;
+
+__device__ __forceinline__ unsigned row_code(int y0, int y1, int Y0, bool steep)
+{
+    unsigned code = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+        const int yb = Y0 + w * kRowsPerThread;
+        const int lo = max(y0 - yb, 0), hi = min(y1 - yb, kRowsPerThread - 1);
+        const unsigned c = (lo > hi) ? kBandMiss : (unsigned)(lo | (hi << 4) | (steep ? 8 : 0));
+        code |= c << (8 * w);
+    }
+    return code;
+}
+
+__device__ __forceinline__ unsigned lane_mask(int x0, int x1, int X0)
+{
+    const int l0 = max(x0 - X0, 0), l1 = min(x1 - X0, kTileW - 1);
+    return (0xffffffffu >> (31 - l1)) & (0xffffffffu << l0);
+}
+
+// One row pair, front to back (render.py:194-196 rearranged): W = F*T, C += W*col, T -= W.
+#define GGS_BLEND_PAIR(k, F_)                 \
+    {                                         \
+        const f2_t Wk = mul2(F_, px.t[k]);    \
+        fma2_acc(px.r[k], Wk, R2);            \
+        fma2_acc(px.g[k], Wk, G2);            \
+        fma2_acc(px.b[k], Wk, B2);            \
+        sub2_acc(px.t[k], Wk);                \
     }
 
-// Blend the staged list into this thread's pixels, in list (= genome) order.
+// Blend the staged list (reverse genome order) into this thread's pixels.  The exponent of the
+// falloff on row i of the thread's column is e(i) = (Cq*qy + t1)*qy + t0 with qy = dy + i
+// (render.py:189-192 with the constants folded at decode time), f = 2^e.
 //
-// Fast path (splat covers all 8 rows of the band, exponent varies gently): the Gaussian along
-// the thread's pixel column is the exponential of a quadratic, so with stride-2 steps
+// Recurrence path (splat covers all 8 rows of the band, exponent varies gently): along the
+// column f is the exponential of a quadratic, so with stride-2 steps
 //     f(i+2) = f(i) * g(i),   g(i+2) = g(i) * h,   h = 2^(8*Cq)
-// the 8 falloffs come from 4 MUFU.EX2 (f0, f1, g0, g1) and packed multiplies, and the three
-// colour blends are FADD2 + FFMA2 on row pairs: 8 issue slots per 2 pixels instead of 20.
-// Slow path (partial band, or a "steep" splat whose exponent changes too fast for the
-// recurrence to stay accurate): the exact per-pixel form, rows selected by uniform branches.
-__device__ __forceinline__ void composite_list(const float4 *__restrict__ list, int cnt, int X,
-                                               float Xf, int Yb, float Ybf, Pixels &px)
+// the 8 falloffs come from 4 MUFU.EX2 (f0, f1, g0, g1) and packed multiplies: 7 packed FMA-pipe
+// operations per row pair in all.
+// Exact path (partial band, or a "steep" splat whose exponent changes too fast for the
+// recurrence to stay accurate): Horner + one MUFU.EX2 per pixel; rows outside [y0, y1] get
+// f = 0 (an exact no-op) through warp-uniform selects, whole pairs are skipped by uniform
+// branches.  Both paths keep the pixel state in packed register pairs.
+__device__ __forceinline__ void composite_list(const float4 *__restrict__ list, int cnt,
+                                               unsigned lanebit, unsigned band_sel, float Xf,
+                                               float Ybf, Pixels &px)
 {
     for (int s = 0; s < cnt; ++s) {
         const float4 q2 = list[3 * s + 2];
-        const int yp = __float_as_int(q2.z);
-        const int y0 = (int)(short)(yp & 0xffff), y1 = yp >> 16;
-        const int lo = max(y0 - Yb, 0), hi = min(y1 - Yb, kRowsPerThread - 1);
-        if (lo > hi) continue;  // splat misses this warp's band (warp-uniform)
+        const unsigned c = __byte_perm(__float_as_uint(q2.z), 0u, band_sel);  // this band's byte
+        if (c == kBandMiss) continue;  // warp-uniform
         const float4 q0 = list[3 * s + 0];
         const float4 q1 = list[3 * s + 1];
-        const int xp = __float_as_int(q2.y);
-        const int x0 = (int)(short)(xp & 0xffff), x1 = xp >> 16;
-        const bool in_x = (X >= x0) & (X <= x1);
+        const bool in_x = (__float_as_uint(q2.y) & lanebit) != 0u;
         const float qx = Xf - q0.x;
         const float t1 = q0.w * qx;                       // Bq*qx
         float t0 = fmaf(q0.z * qx, qx, q1.y);             // A*qx^2 + log2(alpha)
         t0 = in_x ? t0 : -INFINITY;                       // outside [x0,x1]: f = 2^-inf = 0
         const float dy = Ybf - q0.y;
-        const float Cq = q1.x, cr = q1.z, cg = q1.w, cb = q2.x;
-        const float h = q2.w;                             // 2^(8*Cq), or < 0 for a steep splat
-        if (lo == 0 && hi == kRowsPerThread - 1 && h >= 0.0f) {
-            const f2_t QY = pack2(dy, dy + 1.0f);
-            const f2_t E = fma2(fma2(bcast2(Cq), QY, bcast2(t1)), QY, bcast2(t0));
-            const float c4 = 4.0f * Cq;
+        const f2_t QY = pack2(dy, dy + 1.0f);
+        const f2_t CQ2 = bcast2(q1.x), T12 = bcast2(t1), T02 = bcast2(t0);
+        const f2_t R2 = bcast2(q1.z), G2 = bcast2(q1.w), B2 = bcast2(q2.x);
+        if (c == kBandFull) {
+            const f2_t E = fma2(fma2(CQ2, QY, T12), QY, T02);
+            const float c4 = 4.0f * q1.x;
             const f2_t D = fma2(bcast2(c4), QY, bcast2(fmaf(2.0f, t1, c4)));  // e(i+2) - e(i)
             float e0, e1, d0, d1;
             unpack2(E, e0, e1);
             unpack2(D, d0, d1);
             f2_t F = pack2(ex2_approx(e0), ex2_approx(e1));
             f2_t G = pack2(ex2_approx(d0), ex2_approx(d1));
-            const f2_t H2 = bcast2(h), R2 = bcast2(cr), G2 = bcast2(cg), B2 = bcast2(cb);
+            const f2_t H2 = bcast2(q2.w);
 #pragma unroll
-            for (int k = 0; k < kRowsPerThread / 2; ++k) {
-                px.r[k] = fma2(F, sub2(R2, px.r[k]), px.r[k]);
-                px.g[k] = fma2(F, sub2(G2, px.g[k]), px.g[k]);
-                px.b[k] = fma2(F, sub2(B2, px.b[k]), px.b[k]);
-                if (k + 1 < kRowsPerThread / 2) {
-                    F = mul2(F, G);
-                    G = mul2(G, H2);
+            for (int k = 0; k < kPairs; ++k) {
+                GGS_BLEND_PAIR(k, F)
+                if (k + 1 < kPairs) {
+                    mul2_acc(F, G);
+                    mul2_acc(G, H2);
                 }
             }
         } else {
+            const int lo = (int)(c & 7u), hi = (int)(c >> 4);
 #pragma unroll
-            for (int k = 0; k < kRowsPerThread / 2; ++k) {
+            for (int k = 0; k < kPairs; ++k) {
                 if (2 * k + 1 >= lo && 2 * k <= hi) {
-                    float r0, r1, g0, g1, b0, b1;
-                    unpack2(px.r[k], r0, r1);
-                    unpack2(px.g[k], g0, g1);
-                    unpack2(px.b[k], b0, b1);
-                    if (2 * k >= lo) GGS_BLEND1(r0, g0, b0, 2 * k)
-                    if (2 * k + 1 <= hi) GGS_BLEND1(r1, g1, b1, 2 * k + 1)
-                    px.r[k] = pack2(r0, r1);
-                    px.g[k] = pack2(g0, g1);
-                    px.b[k] = pack2(b0, b1);
+                    const f2_t QYk = add2(QY, bcast2((float)(2 * k)));
+                    const f2_t E = fma2(fma2(CQ2, QYk, T12), QYk, T02);
+                    float e0, e1;
+                    unpack2(E, e0, e1);
+                    const float f0 = (2 * k >= lo) ? ex2_approx(e0) : 0.0f;
+                    const float f1 = (2 * k + 1 <= hi) ? ex2_approx(e1) : 0.0f;
+                    const f2_t F = pack2(f0, f1);
+                    GGS_BLEND_PAIR(k, F)
                 }
             }
         }
@@ -160,7 +215,7 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
               int *__restrict__ counter, float *__restrict__ fitness)
 {
     __shared__ float4 s_list[kListCap * 3];
-    __shared__ int s_wcnt[kWarps];
+    __shared__ int s_wcnt[kScanPerThread][kWarps];
     __shared__ float s_red[2 * kWarps];
     __shared__ int s_last;
 
@@ -172,66 +227,94 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
     const int X1 = X0 + kTileW - 1, Y1 = Y0 + kTileH - 1;
     const int X = X0 + lane, Yb = Y0 + warp * kRowsPerThread;
     const float Xf = (float)X, Ybf = (float)Yb;
+    const unsigned lanebit = 1u << lane;
+    const unsigned band_sel = 0x4440u + (unsigned)warp;  // PRMT: byte `warp`, zero-extended
 
     Pixels px;
 #pragma unroll
-    for (int k = 0; k < kRowsPerThread / 2; ++k) {
-        px.r[k] = bcast2(bg_r);  // render.py:236-237
-        px.g[k] = bcast2(bg_g);
-        px.b[k] = bcast2(bg_b);
+    for (int k = 0; k < kPairs; ++k) {
+        px.r[k] = px.g[k] = px.b[k] = bcast2(0.0f);
+        px.t[k] = bcast2(1.0f);
     }
 
     const float4 *recb = rec + (int64_t)b * N * 3;
     const uint2 *boxb = aabb + (int64_t)b * N;
 
+    // Walk the genome from its last splat to its first (front to back).  Slot j of a round
+    // maps thread `tid` to record  top - 1 - (j*kThreads + tid): ascending (j, tid) is
+    // descending genome order, so the ordinary ballot compaction yields the order we need.
     int cnt = 0;
-    for (int base = 0; base < N; base += kThreads) {
-        const int i = base + tid;
-        bool hit = false;
-        if (i < N) {
-            const uint2 box = __ldg(boxb + i);
-            const int x0 = (int)(short)(box.x & 0xffff), x1 = (int)box.x >> 16;
-            const int y0 = (int)(short)(box.y & 0xffff), y1 = (int)box.y >> 16;
-            hit = (x1 >= X0) & (x0 <= X1) & (y1 >= Y0) & (y0 <= Y1);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) s_wcnt[warp] = __popc(m);
-        __syncthreads();
-        int pre = 0, tot = 0;
+    for (int top = N; top > 0; top -= kScanChunk) {
+        bool hit[kScanPerThread];
+        unsigned bal[kScanPerThread];
+        int idx[kScanPerThread];
+        int bx0[kScanPerThread], bx1[kScanPerThread], by0[kScanPerThread], by1[kScanPerThread];
 #pragma unroll
-        for (int w = 0; w < kWarps; ++w) {
-            const int c = s_wcnt[w];
-            pre += (w < warp) ? c : 0;
-            tot += c;
+        for (int j = 0; j < kScanPerThread; ++j) {
+            idx[j] = top - 1 - (j * kThreads + tid);
+            hit[j] = false;
+            bx0[j] = bx1[j] = by0[j] = by1[j] = 0;
+            if (idx[j] >= 0) {
+                const uint2 box = __ldg(boxb + idx[j]);
+                bx0[j] = (int)(short)(box.x & 0xffff);
+                bx1[j] = (int)box.x >> 16;
+                by0[j] = (int)(short)(box.y & 0xffff);
+                by1[j] = (int)box.y >> 16;
+                hit[j] = (bx1[j] >= X0) & (bx0[j] <= X1) & (by1[j] >= Y0) & (by0[j] <= Y1);
+            }
+            bal[j] = __ballot_sync(0xffffffffu, hit[j]);
+            if (lane == 0) s_wcnt[j][warp] = __popc(bal[j]);
         }
-        if (hit) {
-            const int pos = cnt + pre + __popc(m & ((1u << lane) - 1u));
-            const float4 *src = recb + (int64_t)i * 3;
-            s_list[pos * 3 + 0] = __ldg(src + 0);
-            s_list[pos * 3 + 1] = __ldg(src + 1);
-            s_list[pos * 3 + 2] = __ldg(src + 2);
-        }
-        cnt += tot;
         __syncthreads();
-        if (cnt > kListCap - kThreads || base + kThreads >= N) {
-            composite_list(s_list, cnt, X, Xf, Yb, Ybf, px);
+        int run = cnt;
+#pragma unroll
+        for (int j = 0; j < kScanPerThread; ++j) {
+            int pre = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const int c = s_wcnt[j][w];
+                pre += (w < warp) ? c : 0;
+                tot += c;
+            }
+            if (hit[j]) {
+                const int pos = run + pre + __popc(bal[j] & (lanebit - 1u));
+                const float4 *src = recb + (int64_t)idx[j] * 3;
+                float4 q2 = __ldg(src + 2);
+                const bool steep = q2.w < 0.0f;
+                q2.y = __uint_as_float(lane_mask(bx0[j], bx1[j], X0));
+                q2.z = __uint_as_float(row_code(by0[j], by1[j], Y0, steep));
+                s_list[pos * 3 + 0] = __ldg(src + 0);
+                s_list[pos * 3 + 1] = __ldg(src + 1);
+                s_list[pos * 3 + 2] = q2;
+            }
+            run += tot;
+        }
+        cnt = run;
+        __syncthreads();
+        if (cnt > kListCap - kScanChunk || top <= kScanChunk) {
+            composite_list(s_list, cnt, lanebit, band_sel, Xf, Ybf, px);
             cnt = 0;
             __syncthreads();
         }
     }
 
-    // Epilogue: clamp (render.py:252), optional image store, squared error (fitness.py:16-31).
+    // Epilogue: add the background through the remaining transmittance (render.py:236-237),
+    // clamp (render.py:252), optional image store, squared error (fitness.py:16-31).
     float num = 0.0f, den = 0.0f;
     const bool want_fit = (target != nullptr);
 #pragma unroll
     for (int i = 0; i < kRowsPerThread; ++i) {
         const int Y = Yb + i;
-        float pr[2], pg[2], pb[2];
+        float pr[2], pg[2], pb[2], pt[2];
         unpack2(px.r[i >> 1], pr[0], pr[1]);
         unpack2(px.g[i >> 1], pg[0], pg[1]);
         unpack2(px.b[i >> 1], pb[0], pb[1]);
+        unpack2(px.t[i >> 1], pt[0], pt[1]);
         if (X < W && Y < H) {
-            const float cr = clamp01(pr[i & 1]), cg = clamp01(pg[i & 1]), cb = clamp01(pb[i & 1]);
+            const float tr = pt[i & 1];
+            const float cr = clamp01(fmaf(tr, bg_r, pr[i & 1]));
+            const float cg = clamp01(fmaf(tr, bg_g, pg[i & 1]));
+            const float cb = clamp01(fmaf(tr, bg_b, pb[i & 1]));
             const int64_t p = (int64_t)Y * W + X;
             if (images != nullptr) {
                 float *o = images + ((int64_t)b * H * W + p) * 3;
