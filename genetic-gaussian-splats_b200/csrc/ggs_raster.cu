@@ -34,9 +34,24 @@
 namespace ggs {
 namespace {
 
+#ifndef GGS_ILP
+#define GGS_ILP 0
+#endif
+#ifndef GGS_MIN_BLOCKS
+#define GGS_MIN_BLOCKS 7
+#endif
+#ifndef GGS_SATURATE
+#define GGS_SATURATE 1
+#endif
+#ifndef GGS_PREFETCH
+#define GGS_PREFETCH 0
+#endif
+
 constexpr int kPairs = kRowsPerThread / 2;
 constexpr int kScanPerThread = 2;
 constexpr int kScanChunk = kThreads * kScanPerThread;  // records examined per round
+constexpr int kSatEvery = 8;                           // list entries between saturation votes
+constexpr float kOpaque = 2.384185791015625e-07f;      // 2^-22: transmittance counted as zero
 
 __device__ __forceinline__ float ex2_approx(float x)
 {
@@ -151,12 +166,36 @@ __device__ __forceinline__ unsigned lane_mask(int x0, int x1, int X0)
 // recurrence to stay accurate): Horner + one MUFU.EX2 per pixel; rows outside [y0, y1] get
 // f = 0 (an exact no-op) through warp-uniform selects, whole pairs are skipped by uniform
 // branches.  Both paths keep the pixel state in packed register pairs.
-__device__ __forceinline__ void composite_list(const float4 *__restrict__ list, int cnt,
+//
+// Saturation: once every pixel of the band has transmittance below kOpaque, nothing further
+// back can change a pixel by more than kOpaque (colours are in [0,1]), so the warp stops
+// (returns false).  Checked every kSatEvery list entries with one warp vote.
+__device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, int cnt,
                                                unsigned lanebit, unsigned band_sel, float Xf,
                                                float Ybf, Pixels &px)
 {
+#if GGS_PREFETCH
+    float4 q2_next = list[2];  // entry 0; the loop keeps the next entry's q2 in flight
+#endif
     for (int s = 0; s < cnt; ++s) {
+#if GGS_PREFETCH
+        const float4 q2 = q2_next;
+        q2_next = list[3 * min(s + 1, cnt - 1) + 2];
+#else
         const float4 q2 = list[3 * s + 2];
+#endif
+#if GGS_SATURATE
+        if ((s & (kSatEvery - 1)) == kSatEvery - 1) {
+            float t0a, t1a, t2a, t3a, t4a, t5a, t6a, t7a;
+            unpack2(px.t[0], t0a, t1a);
+            unpack2(px.t[1], t2a, t3a);
+            unpack2(px.t[2], t4a, t5a);
+            unpack2(px.t[3], t6a, t7a);
+            const float tmax = fmaxf(fmaxf(fmaxf(t0a, t1a), fmaxf(t2a, t3a)),
+                                     fmaxf(fmaxf(t4a, t5a), fmaxf(t6a, t7a)));
+            if (__all_sync(0xffffffffu, tmax < kOpaque)) return false;
+        }
+#endif
         const unsigned c = __byte_perm(__float_as_uint(q2.z), 0u, band_sel);  // this band's byte
         if (c == kBandMiss) continue;  // warp-uniform
         const float4 q0 = list[3 * s + 0];
@@ -180,6 +219,27 @@ __device__ __forceinline__ void composite_list(const float4 *__restrict__ list, 
             f2_t F = pack2(ex2_approx(e0), ex2_approx(e1));
             f2_t G = pack2(ex2_approx(d0), ex2_approx(d1));
             const f2_t H2 = bcast2(q2.w);
+#if GGS_ILP
+            // recurrence first, then four independent blends: more packed ops in flight
+            f2_t Fk[kPairs];
+            Fk[0] = F;
+#pragma unroll
+            for (int k = 1; k < kPairs; ++k) {
+                Fk[k] = mul2(Fk[k - 1], G);
+                if (k + 1 < kPairs) mul2_acc(G, H2);
+            }
+            f2_t Wk[kPairs];
+#pragma unroll
+            for (int k = 0; k < kPairs; ++k) Wk[k] = mul2(Fk[k], px.t[k]);
+#pragma unroll
+            for (int k = 0; k < kPairs; ++k) fma2_acc(px.r[k], Wk[k], R2);
+#pragma unroll
+            for (int k = 0; k < kPairs; ++k) fma2_acc(px.g[k], Wk[k], G2);
+#pragma unroll
+            for (int k = 0; k < kPairs; ++k) fma2_acc(px.b[k], Wk[k], B2);
+#pragma unroll
+            for (int k = 0; k < kPairs; ++k) sub2_acc(px.t[k], Wk[k]);
+#else
 #pragma unroll
             for (int k = 0; k < kPairs; ++k) {
                 GGS_BLEND_PAIR(k, F)
@@ -188,6 +248,7 @@ __device__ __forceinline__ void composite_list(const float4 *__restrict__ list, 
                     mul2_acc(G, H2);
                 }
             }
+#endif
         } else {
             const int lo = (int)(c & 7u), hi = (int)(c >> 4);
 #pragma unroll
@@ -205,9 +266,10 @@ __device__ __forceinline__ void composite_list(const float4 *__restrict__ list, 
             }
         }
     }
+    return true;
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS)
 raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, int N, int H, int W,
               int ntx, int ntiles, float bg_r, float bg_g, float bg_b,
               const float *__restrict__ target, const float *__restrict__ mask, int mode,
@@ -230,12 +292,16 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
     const unsigned lanebit = 1u << lane;
     const unsigned band_sel = 0x4440u + (unsigned)warp;  // PRMT: byte `warp`, zero-extended
 
+    // Transmittance starts at 1 inside the image and at 0 outside it: pixels beyond the image
+    // edge then take no colour and never keep a band from saturating.
     Pixels px;
 #pragma unroll
     for (int k = 0; k < kPairs; ++k) {
         px.r[k] = px.g[k] = px.b[k] = bcast2(0.0f);
-        px.t[k] = bcast2(1.0f);
+        px.t[k] = pack2((X < W && Yb + 2 * k < H) ? 1.0f : 0.0f,
+                        (X < W && Yb + 2 * k + 1 < H) ? 1.0f : 0.0f);
     }
+    bool live = true;  // warp-uniform: this band still has a non-opaque pixel
 
     const float4 *recb = rec + (int64_t)b * N * 3;
     const uint2 *boxb = aabb + (int64_t)b * N;
@@ -292,9 +358,10 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
         cnt = run;
         __syncthreads();
         if (cnt > kListCap - kScanChunk || top <= kScanChunk) {
-            composite_list(s_list, cnt, lanebit, band_sel, Xf, Ybf, px);
+            if (live) live = composite_list(s_list, cnt, lanebit, band_sel, Xf, Ybf, px);
             cnt = 0;
-            __syncthreads();
+            // all four bands opaque: the rest of the genome is hidden behind what is drawn
+            if (__syncthreads_and(!live)) break;
         }
     }
 

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libggs_b200.so")
+LIB_PATH = os.environ.get("GGS_B200_LIB") or os.path.join(_PKG_ROOT, "lib", "libggs_b200.so")
 
 OK = 0
 LAYOUT_AXES_ANGLE, LAYOUT_CHOLESKY = 0, 1
