@@ -1,0 +1,126 @@
+"""Genetic-algorithm loop (reference: modules/algorithm.py:17-195), same entry point and
+return value, restructured around a population tensor that stays resident on the device:
+selection, crossover, mutation and elitism are batched tensor ops (modules/genetic.py), the
+evaluation is the fused CUDA path, and the only host transfer per generation is the fitness
+vector.  Two reference quirks are dropped because they cannot change results: elites are not
+re-evaluated (the evaluation is deterministic, algorithm.py:134) -- their stored fitness is
+reused -- and the offspring that elitism would discard are still evaluated (one launch)."""
+from statistics import median
+from typing import Tuple
+
+import torch
+import torch.nn.functional as F
+
+try:
+    from tqdm.auto import tqdm
+except Exception:  # tqdm is optional
+    def tqdm(it, **_):
+        return it
+
+from modules.fitness import fitness_many
+from modules.genetic import crossover_population, mutate_population, tournament_indices
+from modules.mask import compute_importance_mask
+from modules.population import new_population
+from modules.utils import (_anneal_factor, prewarm_renderer, save_curves_csv, save_frame_png,
+                           save_loss_curve_png)
+
+
+def prepare_target(target_img_uint8: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """float32 [H,W,3] in [0,1], bilinearly resized to the work size (algorithm.py:33-39)."""
+    t = target_img_uint8.to(torch.float32)
+    if t.max() > 1.5:
+        t = t / 255.0
+    if t.shape[0] != H or t.shape[1] != W:
+        t = F.interpolate(t.permute(2, 0, 1).unsqueeze(0), size=(H, W), mode='bilinear',
+                          align_corners=False)[0].permute(1, 2, 0)
+    return t.contiguous()
+
+
+@torch.no_grad()
+def genetic_approx(target_img_uint8: torch.Tensor,
+                   H: int, W: int, device,
+                   pop_size: int, n_splats: int, generations: int,
+                   tour_k: int, elite_k: int, cxpb: float, mutpb: float,
+                   mut_sigma_max: dict, mut_sigma_min: dict, schedule: str,
+                   min_scale_splats: float, max_scale_splats: float,
+                   k_sigma: float, mask_strength: float, boost_only: bool,
+                   save_video: bool = False, frame_every: int = 5000,
+                   video_dir: str = "", prefix: str = "ga",
+                   loss_png_path: str = "",
+                   loss_csv_path: str = "",
+                   loss_log_y: bool = False) -> Tuple[torch.Tensor, float]:
+    t = prepare_target(target_img_uint8, H, W)
+    imp_mask = compute_importance_mask(t, H, W, edge_scales=(1, 2, 4), w_edge=0.7, w_var=0.3,
+                                       gamma=0.7, floor=0.15, smooth=3,
+                                       strength=mask_strength).to(device)
+    target = t.to(device)          # target and mask stay resident for the whole run
+    prewarm_renderer(H, W, k_sigma, device)
+
+    def evaluate(pop_tensor: torch.Tensor) -> torch.Tensor:
+        return fitness_many(pop_tensor, target, H, W, k_sigma, device, tile=32,
+                            weight_mask=imp_mask, boost_only=boost_only)
+
+    pop = new_population(pop_size, n_splats, H, W, min_scale_splats, max_scale_splats, device=device)
+    fit = evaluate(pop)
+    fit_host = fit.cpu().tolist()
+
+    best_idx = min(range(pop_size), key=fit_host.__getitem__)
+    best_ind, best_fit = pop[best_idx].clone(), fit_host[best_idx]
+    no_improve = 0
+    curves = {"best": [float(best_fit)], "mean": [sum(fit_host) / len(fit_host)],
+              "median": [float(median(fit_host))]}
+
+    pad = len(str(generations))
+    if save_video:
+        save_frame_png(0, best_ind, pad, prefix, video_dir, H, W, k_sigma, device, save_video)
+
+    n_elite = max(1, elite_k)
+    pbar = tqdm(range(1, generations + 1), desc="GA generations", leave=True)
+    try:
+        for gen in pbar:
+            # selection -> shuffle -> crossover -> mutation, all on the resident tensor
+            parents = pop[tournament_indices(fit, pop_size, k=tour_k)]
+            parents = parents[torch.randperm(pop_size, device=pop.device)]
+            offspring = crossover_population(parents, cxpb)
+            mutate_population(offspring, gen, generations, schedule, mut_sigma_max, mut_sigma_min,
+                              mutpb, H, W, min_scale_splats, max_scale_splats)
+            off_fit = evaluate(offspring)
+
+            # elitism: the n_elite best of the current generation survive unchanged
+            elite_idx = torch.argsort(fit, stable=True)[:n_elite]
+            keep = pop_size - n_elite
+            pop = torch.cat([pop[elite_idx], offspring[:keep]], dim=0)
+            fit = torch.cat([fit[elite_idx], off_fit[:keep]], dim=0)
+            fit_host = fit.cpu().tolist()
+
+            gbest = min(range(pop_size), key=fit_host.__getitem__)
+            if fit_host[gbest] + 1e-10 < best_fit:
+                best_fit, best_ind, no_improve = fit_host[gbest], pop[gbest].clone(), 0
+            else:
+                no_improve += 1
+            curves["best"].append(float(best_fit))
+            curves["mean"].append(sum(fit_host) / len(fit_host))
+            curves["median"].append(float(median(fit_host)))
+
+            if save_video and gen % max(1, frame_every) == 0:
+                save_frame_png(gen, best_ind, pad, prefix, video_dir, H, W, k_sigma, device, save_video)
+            if hasattr(pbar, "set_postfix"):
+                pbar.set_postfix(best_mse=f"{best_fit:.6f}", stale=no_improve,
+                                 sigma_fac=f"{_anneal_factor(gen, generations, schedule):.3f}")
+    except KeyboardInterrupt:
+        print("\n[Interrupted] Returning current best individual...", flush=True)
+    finally:
+        if hasattr(pbar, "close"):
+            pbar.close()
+
+    try:
+        save_loss_curve_png(curves, loss_png_path, title=f"{prefix} fitness", xlabel="Generation",
+                            ylabel="MSE", log_y=loss_log_y, dpi=144)
+        save_curves_csv(curves, loss_csv_path)
+        if loss_png_path:
+            print(f"Saved loss plot to {loss_png_path}")
+        if loss_csv_path:
+            print(f"Saved loss CSV to {loss_csv_path}")
+    except Exception as e:
+        print(f"[warn] Could not save loss curves: {e}")
+    return best_ind.cpu(), best_fit

@@ -1,0 +1,146 @@
+"""Simulated annealing (reference: modules/annealing.py:29-190), same entry point.
+
+The reference runs `tries_per_iter` strictly sequential tries per iteration, each a B=1
+evaluation.  Here all tries of an iteration are proposed from the current state and evaluated
+in ONE launch (B = tries_per_iter, BASELINE config 2 "batched neighbour proposals"), then the
+Metropolis test is applied to them in order.  This changes the chain slightly -- a later try no
+longer starts from an earlier accepted try of the same iteration -- and is switched off with
+batch_neighbors=False, which reproduces the reference's sequential scheme."""
+from __future__ import annotations
+
+import math
+import random
+from typing import Tuple
+
+import torch
+
+try:
+    from tqdm.auto import tqdm
+except Exception:
+    def tqdm(it, **_):
+        return it
+
+from modules.algorithm import prepare_target
+from modules.fitness import fitness_many
+from modules.genetic import mutate_population
+from modules.mask import compute_importance_mask
+from modules.population import new_individual
+from modules.utils import (_anneal_factor, prewarm_renderer, save_curves_csv, save_frame_png,
+                           save_loss_curve_png)
+
+_ensure_hw = prepare_target  # the reference's private name (annealing.py:19-26)
+
+
+def _temp_schedule(kind: str, T0: float, i: int, total: int) -> float:
+    """Temperature at step i of `total` (annealing.py:29-44)."""
+    n = max(1, total)
+    p = i / n
+    if kind == "linear":
+        return max(1e-12, T0 * (1.0 - p))
+    if kind == "cosine":
+        return max(1e-12, T0 * 0.5 * (1.0 + math.cos(math.pi * p)))
+    if kind == "log":
+        return max(1e-12, T0 / (1.0 + math.log(1.0 + 9.0 * i)))
+    if kind == "cauchy":
+        return max(1e-12, T0 / (1.0 + i))
+    return T0 * ((0.01 ** (1.0 / n)) ** i)   # "exp" and anything unknown
+
+
+@torch.no_grad()
+def simulated_annealing(
+    target_img_uint8: torch.Tensor,
+    H: int, W: int, device,
+    n_splats: int,
+    mutpb: float,
+    mut_sigma_max: dict,
+    mut_sigma_min: dict,
+    sigma_schedule: str,
+    min_scale_splats: float,
+    max_scale_splats: float,
+    k_sigma: float,
+    mask_strength: float,
+    boost_only: bool,
+    iterations: int,
+    temp0: float,
+    temp_schedule: str,
+    tries_per_iter: int = 1,
+    save_video: bool = False,
+    frame_every: int = 10_000,
+    video_dir: str = "",
+    prefix: str = "sa",
+    loss_png_path: str = "",
+    loss_csv_path: str = "",
+    loss_log_y: bool = False,
+    batch_neighbors: bool = True,
+) -> Tuple[torch.Tensor, float]:
+    """Minimises the (masked) MSE energy; returns (best axes-angle individual on CPU, best MSE)."""
+    t = prepare_target(target_img_uint8, H, W)
+    target = t.to(device)
+    imp_mask = compute_importance_mask(t, H, W, edge_scales=(1, 2, 4), w_edge=0.7, w_var=0.3,
+                                       gamma=0.7, floor=0.15, smooth=3,
+                                       strength=mask_strength).to(device)
+    prewarm_renderer(H, W, k_sigma, device)
+
+    def energy(batch: torch.Tensor):
+        return fitness_many(batch, target, H, W, k_sigma, device, tile=32, weight_mask=imp_mask,
+                            boost_only=boost_only).cpu().tolist()
+
+    def propose(state: torch.Tensor, count: int, it: int) -> torch.Tensor:
+        nb = state.unsqueeze(0).repeat(count, 1, 1)
+        return mutate_population(nb, it, iterations, sigma_schedule, mut_sigma_max, mut_sigma_min,
+                                 mutpb, H, W, min_scale_splats, max_scale_splats)
+
+    curr = new_individual(n_splats, H, W, min_scale_splats, max_scale_splats, device=device)
+    e_curr = float(energy(curr.unsqueeze(0))[0])
+    best, best_fit = curr.clone(), e_curr
+    curves = {"best": [best_fit], "current": [e_curr]}
+
+    pad = len(str(iterations))
+    if save_video:
+        save_frame_png(0, best, pad, prefix, video_dir, H, W, k_sigma, device, save_video)
+
+    tries = max(1, tries_per_iter)
+    pbar = tqdm(range(iterations), desc="SA iterations", leave=True)
+    try:
+        for it in pbar:
+            T = _temp_schedule(temp_schedule, temp0, it, iterations)
+            accepted_any = False
+            if batch_neighbors:
+                neighbours = propose(curr, tries, it)
+                energies = energy(neighbours)
+            for k in range(tries):
+                if batch_neighbors:
+                    cand, e_new = neighbours[k], float(energies[k])
+                else:
+                    cand = propose(curr, 1, it)[0]
+                    e_new = float(energy(cand.unsqueeze(0))[0])
+                dE = e_new - e_curr
+                if dE <= 0.0 or (T > 0.0 and random.random() < math.exp(-dE / T)):
+                    curr, e_curr, accepted_any = cand.clone(), e_new, True
+                if e_curr + 1e-12 < best_fit:
+                    best_fit, best = e_curr, curr.clone()
+            curves["best"].append(best_fit)
+            curves["current"].append(e_curr)
+            if save_video and (it + 1) % max(1, frame_every) == 0:
+                save_frame_png(it + 1, best, pad, prefix, video_dir, H, W, k_sigma, device, save_video)
+            if hasattr(pbar, "set_postfix"):
+                pbar.set_postfix(best_mse=f"{best_fit:.6f}", curr_mse=f"{e_curr:.6f}", T=f"{T:.4g}",
+                                 accepted="Y" if accepted_any else "N",
+                                 sigma_fac=f"{_anneal_factor(it, iterations, sigma_schedule):.3f}")
+    except KeyboardInterrupt:
+        print("\n[Interrupted] Returning current best...", flush=True)
+    finally:
+        if hasattr(pbar, "close"):
+            pbar.close()
+
+    try:
+        save_loss_curve_png(curves, loss_png_path, title=f"{prefix} energy (MSE)",
+                            xlabel="Iteration", ylabel="MSE", log_y=loss_log_y, dpi=144)
+        save_curves_csv(curves, loss_csv_path)
+        if loss_png_path:
+            print(f"Saved loss plot to {loss_png_path}")
+        if loss_csv_path:
+            print(f"Saved loss CSV to {loss_csv_path}")
+    except Exception as e:
+        print(f"[warn] Could not save SA curves: {e}")
+    return best.cpu(), float(best_fit)
