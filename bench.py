@@ -53,6 +53,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# Libraries (NCCL prints its version banner) may write to fd 1; the contract is ONE JSON line
+# on stdout, so everything but that line is sent to stderr at the file-descriptor level.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def dist_env():
     return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
             int(os.environ.get("WORLD_SIZE", "1")))
@@ -177,7 +188,7 @@ def run_reference(args, wl):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -333,7 +344,7 @@ def run_ours(args, wl):
             "gpu_launches": 2 * K,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
