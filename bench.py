@@ -64,6 +64,22 @@ def emit(line: dict):
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
+def ncu_traffic(workload: str, population: int):
+    """dram bytes read + written per raster launch, from the committed ncu capture of this
+    workload (profiles/rNN_traffic.json); None when no capture matches."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    for name in sorted(os.listdir(pdir)) if os.path.isdir(pdir) else []:
+        if name.endswith("_traffic.json"):
+            try:
+                rec = json.load(open(os.path.join(pdir, name)))
+            except Exception:
+                continue
+            if rec.get("workload") == workload and rec.get("population") == population:
+                best = rec["dram_bytes_read"] + rec["dram_bytes_write"]
+    return best
+
+
 def dist_env():
     return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
             int(os.environ.get("WORLD_SIZE", "1")))
@@ -302,7 +318,7 @@ def run_ours(args, wl):
             "bound": "fp32", "kernel": "ggs::raster_kernel", "achieved": achieved,
             "peak": NOMINAL_FP32_TFLOPS, "unit": "TFLOP/s",
             "frac": None if achieved is None else achieved / NOMINAL_FP32_TFLOPS,
-            "traffic": None,
+            "traffic": ncu_traffic(args.workload, P),
             "peak_source": "nominal 148 SM x 128 lanes x 2 x clocks.max.sm 1965 MHz; "
                            "MEASURED_PEAKS.json has no fp32 entry (HBM and bf16 tensor only)",
             "measured_ffma_tflops": peaks["ffma_tflops"],
@@ -358,12 +374,23 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c3")
     ap.add_argument("--population", type=int, default=None, help="override candidates per GPU")
+    ap.add_argument("--side", type=int, default=None, help="override H = W (roofline sweep)")
+    ap.add_argument("--splats", type=int, default=None, help="override splats per candidate")
+    ap.add_argument("--pool", type=int, default=None, help="distinct populations rotated (default 4)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     wl = dict(WORKLOADS[args.workload])
     if args.population:
         wl["P"] = args.population
+    if args.side or args.splats:
+        wl["H"] = wl["W"] = args.side or wl["H"]
+        wl["N"] = args.splats or wl["N"]
+        wl["desc"] = (f"sweep point: {wl['H']}x{wl['W']}, {wl['N']} splats, population {wl['P']} "
+                      f"per GPU, mask-weighted fitness")
+    if args.pool:
+        global POOL
+        POOL = args.pool
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] note: fewer than 3 warm-up steps requested")
     return run_reference(args, wl) if args.impl == "reference" else run_ours(args, wl)
