@@ -88,64 +88,72 @@ def dist_env():
 # --------------------------------------------------------------------------- clocks
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons sampled WHILE the timed region runs: NVML polled
+    from a thread every few milliseconds (nvidia-smi once as a fallback)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, gpu_id: str):
-        self.gpu_id, self.proc, self.lines = gpu_id, None, []
+    def __init__(self, uuid: str, index: int):
+        self.uuid, self.index = uuid, index
+        self.samples, self.stop_flag, self.thread, self.h = [], threading.Event(), None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if isinstance(uuid, str) else uuid)
+            except Exception:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nv = pynvml
+        except Exception as e:
+            log(f"[bench] NVML unavailable ({e}); falling back to one nvidia-smi query")
 
-    def _cmd(self, loop: bool):
-        cmd = ["nvidia-smi", "-i", self.gpu_id, f"--query-gpu={self.FIELDS}",
-               "--format=csv,noheader,nounits"]
-        return cmd + (["-lms", "50"] if loop else [])
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(self._cmd(True), stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception as e:  # nvidia-smi missing: report it, do not fail the bench
-            log(f"[bench] clock sampler unavailable: {e}")
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.h is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
 
     def stop(self) -> dict:
-        if self.proc is not None:
-            self.proc.terminate()
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+        if self.samples:
+            sm = [s[0] for s in self.samples]
+            mask = 0
+            for s_ in self.samples:
+                mask |= int(s_[2])
             try:
-                self.proc.wait(timeout=5)
+                mx = self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)
             except Exception:
-                self.proc.kill()
-        lines = list(self.lines)
-        if not lines:
-            try:
-                lines = subprocess.run(self._cmd(False), capture_output=True, text=True,
-                                       timeout=20).stdout.strip().splitlines()
-            except Exception:
-                lines = []
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for ln in lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-                pw.append(float(parts[2]))
-            except ValueError:
-                continue
-            for name, val in zip(names, parts[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+                mx = max(sm)
+            return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(mx),
+                    "power_w_max": float(max(s[1] for s in self.samples)),
+                    "reasons": sorted(n for bit, n in self.REASONS.items() if mask & bit),
+                    "samples": len(sm), "how": "NVML polled every ~4 ms during the timed region"}
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index),
+                                  "--query-gpu=clocks.sm,clocks.max.sm,power.draw",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                 timeout=20).stdout.strip().split(",")
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]),
+                    "power_w_max": float(out[2]), "reasons": [], "samples": 1,
+                    "how": "one nvidia-smi query after the timed region"}
+        except Exception:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
-                "power_w_max": float(max(pw)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ------------------------------------------------------------------ CPU (reference) arm
@@ -266,13 +274,13 @@ def run_ours(args, wl):
     torch.cuda.synchronize(dev)
 
     props = torch.cuda.get_device_properties(dev)
-    sampler = ClockSampler("GPU-" + str(props.uuid) if hasattr(props, "uuid") else str(local_rank))
-    sampler.start()
+    sampler = ClockSampler("GPU-" + str(props.uuid) if hasattr(props, "uuid") else "", local_rank)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
     ggs_b200.timing_enable(True)
+    sampler.start()
     e0.record()
     last = None
     for i in range(K):
@@ -286,6 +294,10 @@ def run_ours(args, wl):
     ggs_b200.timing_enable(False)
     clocks = sampler.stop()
     assert torch.isfinite(last).all()
+
+    # ---- work actually done (instrumented kernel, outside the timed region)
+    work = ggs_b200.count_evaluated_pairs(
+        lambda: ggs_b200.fitness(pool[0], target, H, W, 3.0, weight_mask=mask), device=dev)
 
     # ---- end to end: host buffers through the C ABI, H2D + D2H inside the timed region
     he = ggs_b200.HostEvaluator(t_np, m_np, device=local_rank)
@@ -327,6 +339,12 @@ def run_ours(args, wl):
             "frac_of_measured_ffma": None if achieved is None else achieved / peaks["ffma_tflops"],
             "algorithmic_flop_per_launch": float(np.mean(flop_per_launch)),
             "pairs_per_candidate": float(np.mean(pairs)) / P,
+            "evaluated_pairs_per_candidate": work["pairs"] / P,
+            "evaluated_over_algorithmic": work["pairs"] / max(1, pairs[0]),
+            "evaluated_on_exact_path": work["exact_pairs"] / max(1, work["pairs"]),
+            "note": "evaluated pairs = lanes x rows the kernel really blended (instrumented run): "
+                    "above the algorithmic count by the columns of a 32-wide tile outside a "
+                    "splat's AABB, below it where bands stop once opaque (transmittance < 2^-22)",
             "raster_ms_per_launch": kt["raster_ms"] / max(1, kt["evaluations"]),
             "decode_ms_per_launch": kt["decode_ms"] / max(1, kt["evaluations"]),
             "raster_share_of_step": kt["raster_ms"] / ms if ms > 0 else None,

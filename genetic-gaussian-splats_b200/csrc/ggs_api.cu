@@ -96,6 +96,7 @@ struct TimingLog {
     cudaEvent_t ev[kCap][3];
 };
 static TimingLog g_timing;
+static unsigned long long *g_stats = nullptr;  // ggs_stats_target(): device counters or NULL
 
 static cudaEvent_t *timing_slot()
 {
@@ -135,7 +136,7 @@ static int evaluate(const float *d_genomes, int layout, int B, int N, int cols, 
                            nullptr, nullptr, ws.counter, B, stream));
     if (ev) GGS_CUDA(cudaEventRecord(ev[1], stream));
     GGS_CUDA(launch_raster(ws, B, N, H, W, bg, d_target, d_mask, mode, beta, d_fitness, d_images,
-                           stream));
+                           g_stats, stream));
     if (ev) GGS_CUDA(cudaEventRecord(ev[2], stream));
     return GGS_OK;
 }
@@ -392,6 +393,12 @@ int ggs_ctx_fitness_host(ggs_ctx *c, const float *h_genomes, int layout, int B, 
     GGS_CUDA(cudaMemcpyAsync(h_fitness, c->d_fitness, (size_t)B * sizeof(float),
                              cudaMemcpyDeviceToHost, c->stream[0]));
     GGS_CUDA(cudaStreamSynchronize(c->stream[0]));
+    return GGS_OK;
+}
+
+int ggs_stats_target(unsigned long long *d_counters2)
+{
+    g_stats = d_counters2;
     return GGS_OK;
 }
 

@@ -60,7 +60,8 @@ cudaError_t launch_encode(const float *d_axes, int64_t rows, int cols, float *d_
 // raster.cu
 cudaError_t launch_raster(const Workspace &ws, int B, int N, int H, int W, const float bg[3],
                           const float *d_target, const float *d_mask, int mode, float beta,
-                          float *d_fitness, float *d_images, cudaStream_t stream);
+                          float *d_fitness, float *d_images, unsigned long long *d_stats,
+                          cudaStream_t stream);
 
 // probe.cu
 cudaError_t probe_peaks(float *h_out5);

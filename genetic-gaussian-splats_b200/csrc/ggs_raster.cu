@@ -170,9 +170,10 @@ __device__ __forceinline__ unsigned lane_mask(int x0, int x1, int X0)
 // Saturation: once every pixel of the band has transmittance below kOpaque, nothing further
 // back can change a pixel by more than kOpaque (colours are in [0,1]), so the warp stops
 // (returns false).  Checked every kSatEvery list entries with one warp vote.
+template <bool kStats>
 __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, int cnt,
                                                unsigned lanebit, unsigned band_sel, float Xf,
-                                               float Ybf, Pixels &px)
+                                               float Ybf, Pixels &px, unsigned (&work)[2])
 {
 #if GGS_PREFETCH
     float4 q2_next = list[2];  // entry 0; the loop keeps the next entry's q2 in flight
@@ -219,6 +220,7 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
             f2_t F = pack2(ex2_approx(e0), ex2_approx(e1));
             f2_t G = pack2(ex2_approx(d0), ex2_approx(d1));
             const f2_t H2 = bcast2(q2.w);
+            if (kStats) work[0] += kPairs;
 #if GGS_ILP
             // recurrence first, then four independent blends: more packed ops in flight
             f2_t Fk[kPairs];
@@ -261,6 +263,7 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
                     const float f0 = (2 * k >= lo) ? ex2_approx(e0) : 0.0f;
                     const float f1 = (2 * k + 1 <= hi) ? ex2_approx(e1) : 0.0f;
                     const f2_t F = pack2(f0, f1);
+                    if (kStats) work[1] += 1;
                     GGS_BLEND_PAIR(k, F)
                 }
             }
@@ -269,13 +272,16 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
     return true;
 }
 
+template <bool kStats>
 __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS)
 raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, int N, int H, int W,
               int ntx, int ntiles, float bg_r, float bg_g, float bg_b,
               const float *__restrict__ target, const float *__restrict__ mask, int mode,
               float beta, float *__restrict__ images, float2 *__restrict__ partial,
-              int *__restrict__ counter, float *__restrict__ fitness)
+              int *__restrict__ counter, float *__restrict__ fitness,
+              unsigned long long *__restrict__ stats)
 {
+    unsigned work[2] = {0u, 0u};  // kStats: row pairs blended on the recurrence / exact path
     __shared__ float4 s_list[kListCap * 3];
     __shared__ int s_wcnt[kScanPerThread][kWarps];
     __shared__ float s_red[2 * kWarps];
@@ -358,7 +364,7 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
         cnt = run;
         __syncthreads();
         if (cnt > kListCap - kScanChunk || top <= kScanChunk) {
-            if (live) live = composite_list(s_list, cnt, lanebit, band_sel, Xf, Ybf, px);
+            if (live) live = composite_list<kStats>(s_list, cnt, lanebit, band_sel, Xf, Ybf, px, work);
             cnt = 0;
             // all four bands opaque: the rest of the genome is hidden behind what is drawn
             if (__syncthreads_and(!live)) break;
@@ -402,6 +408,11 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
                 den += w;
             }
         }
+    }
+    if (kStats && lane == 0) {
+        // pixel-splat pairs actually evaluated: 64 lanes-rows per blended row pair
+        atomicAdd(stats + 0, (unsigned long long)work[0]);
+        atomicAdd(stats + 1, (unsigned long long)work[1]);
     }
     if (!want_fit) return;
 
@@ -461,15 +472,21 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
 
 cudaError_t launch_raster(const Workspace &ws, int B, int N, int H, int W, const float bg[3],
                           const float *d_target, const float *d_mask, int mode, float beta,
-                          float *d_fitness, float *d_images, cudaStream_t stream)
+                          float *d_fitness, float *d_images, unsigned long long *d_stats,
+                          cudaStream_t stream)
 {
     if (B <= 0) return cudaSuccess;
     const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
     const int64_t grid = (int64_t)B * ntiles;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    raster_kernel<<<(unsigned)grid, kThreads, 0, stream>>>(
-        ws.rec, ws.aabb, N, H, W, ntx, ntiles, bg[0], bg[1], bg[2], d_target, d_mask, mode, beta,
-        d_images, ws.partial, ws.counter, d_fitness);
+    if (d_stats != nullptr)
+        raster_kernel<true><<<(unsigned)grid, kThreads, 0, stream>>>(
+            ws.rec, ws.aabb, N, H, W, ntx, ntiles, bg[0], bg[1], bg[2], d_target, d_mask, mode,
+            beta, d_images, ws.partial, ws.counter, d_fitness, d_stats);
+    else
+        raster_kernel<false><<<(unsigned)grid, kThreads, 0, stream>>>(
+            ws.rec, ws.aabb, N, H, W, ntx, ntiles, bg[0], bg[1], bg[2], d_target, d_mask, mode,
+            beta, d_images, ws.partial, ws.counter, d_fitness, nullptr);
     return cudaGetLastError();
 }
 

@@ -148,6 +148,21 @@ def probe_peaks() -> dict:
             "sm_count": int(out[3]), "sm_clock_mhz": out[4]}
 
 
+def count_evaluated_pairs(run, device=None) -> dict:
+    """Run `run()` (any evaluation) on the instrumented raster kernel and return the number
+    of (pixel, splat) pairs it actually evaluated, split by path."""
+    dev = _cuda_device(device)
+    counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    check(lib().ggs_stats_target(counters.data_ptr()), "ggs_stats_target")
+    try:
+        run()
+        torch.cuda.synchronize(dev)
+    finally:
+        check(lib().ggs_stats_target(None), "ggs_stats_target")
+    rec, exact = (int(v) * 64 for v in counters.tolist())
+    return {"recurrence_pairs": rec, "exact_pairs": exact, "pairs": rec + exact}
+
+
 def timing_enable(enable: bool = True) -> None:
     check(lib().ggs_timing_enable(1 if enable else 0), "ggs_timing_enable")
 

@@ -151,6 +151,16 @@ int ggs_probe_peaks(float *h_out5);
  * Not thread-safe; meant for a single benchmarking thread.
  */
 int ggs_timing_enable(int enable);
+
+/*
+ * Work counters for bench.py's roofline.  While d_counters2 (2 x uint64 on the device, zeroed
+ * by the caller) is set, evaluations run an instrumented copy of the raster kernel that adds
+ * the number of 2-row x 32-column pixel blocks it blended on the recurrence path to
+ * d_counters2[0] and on the exact path to d_counters2[1] (x 64 = pixel-splat pairs actually
+ * evaluated, as opposed to the algorithmic in-AABB pairs).  Pass NULL to switch back to the
+ * production kernel.  Not thread-safe.
+ */
+int ggs_stats_target(unsigned long long *d_counters2);
 int ggs_timing_read(float *h_decode_ms, float *h_raster_ms, int *h_evaluations);
 
 #ifdef __cplusplus
