@@ -29,6 +29,7 @@ SOURCES = {
     # ptxas -O3 renames the packed (64-bit) pixel accumulators out of place and pays ~20
     # MOV/IMAD.MOV per splat to move them back; -O1 keeps FFMA2/FADD2 in place (checked in SASS)
     "ggs_raster.cu": ["-Xptxas", "-O1"],
+    "ggs_breed.cu": [],
     "ggs_probe.cu": [],
     "ggs_api.cu": [],
 }

@@ -396,6 +396,29 @@ int ggs_ctx_fitness_host(ggs_ctx *c, const float *h_genomes, int layout, int B, 
     return GGS_OK;
 }
 
+int ggs_ga_breed(const float *d_population, const float *d_fitness, int P, int N, int cols,
+                 float *d_offspring, int tour_k, float cxpb, float mutpb, const float *h_sigma6,
+                 float log_scale_lo, float log_scale_hi, uint64_t seed, uint32_t generation,
+                 void *stream)
+{
+    if (P < 0 || N < 0 || cols < 9 || tour_k < 1 || h_sigma6 == nullptr) {
+        set_error("ggs_ga_breed: bad arguments (P=%d N=%d cols=%d tour_k=%d)", P, N, cols, tour_k);
+        return GGS_EINVAL;
+    }
+    if (P > 0 && N > 0 && (!d_population || !d_fitness || !d_offspring)) {
+        set_error("ggs_ga_breed: NULL buffer");
+        return GGS_EINVAL;
+    }
+    if (d_population == d_offspring && P > 0) {
+        set_error("ggs_ga_breed: offspring must not alias the population");
+        return GGS_EINVAL;
+    }
+    GGS_CUDA(launch_breed(d_population, d_fitness, P, N, cols, d_offspring, tour_k, cxpb, mutpb,
+                          h_sigma6, log_scale_lo, log_scale_hi, seed, generation,
+                          static_cast<cudaStream_t>(stream)));
+    return GGS_OK;
+}
+
 int ggs_stats_target(unsigned long long *d_counters2)
 {
     g_stats = d_counters2;

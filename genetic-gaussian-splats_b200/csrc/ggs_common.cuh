@@ -63,6 +63,12 @@ cudaError_t launch_raster(const Workspace &ws, int B, int N, int H, int W, const
                           float *d_fitness, float *d_images, unsigned long long *d_stats,
                           cudaStream_t stream);
 
+// breed.cu
+cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int N, int cols,
+                         float *d_offspring, int tour_k, float cxpb, float mutpb,
+                         const float sigma6[6], float log_lo, float log_hi, uint64_t seed,
+                         uint32_t generation, cudaStream_t stream);
+
 // probe.cu
 cudaError_t probe_peaks(float *h_out5);
 

@@ -148,6 +148,31 @@ def probe_peaks() -> dict:
             "sm_count": int(out[3]), "sm_clock_mhz": out[4]}
 
 
+SIGMA_ORDER = ("xy", "alog", "blog", "theta", "rgb", "alpha")
+
+
+@torch.no_grad()
+def breed(population: torch.Tensor, fitness_values: torch.Tensor, sigma: dict, *, tour_k: int,
+          cxpb: float, mutpb: float, log_scale_lo: float, log_scale_hi: float, seed: int,
+          generation: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One GA breeding step on device (ggs_ga_breed): [P,N,C>=9] + [P] -> offspring [P,N,9]."""
+    dev = _cuda_device(population.device)
+    pop = _as_f32(population, dev)
+    fit = _as_f32(fitness_values, dev)
+    P, N, C = pop.shape
+    assert fit.shape == (P,)
+    if out is None:
+        out = torch.empty((P, N, 9), dtype=torch.float32, device=dev)
+    assert out.shape == (P, N, 9) and out.is_contiguous() and out.data_ptr() != pop.data_ptr()
+    sig = (ctypes.c_float * 6)(*[float(sigma[k]) for k in SIGMA_ORDER])
+    with torch.cuda.device(dev):
+        check(lib().ggs_ga_breed(pop.data_ptr(), fit.data_ptr(), P, N, C, out.data_ptr(),
+                                 int(tour_k), float(cxpb), float(mutpb), sig, float(log_scale_lo),
+                                 float(log_scale_hi), int(seed) & (2**64 - 1),
+                                 int(generation) & 0xffffffff, _stream_ptr(dev)), "ggs_ga_breed")
+    return out
+
+
 def count_evaluated_pairs(run, device=None) -> dict:
     """Run `run()` (any evaluation) on the instrumented raster kernel and return the number
     of (pixel, splat) pairs it actually evaluated, split by path."""

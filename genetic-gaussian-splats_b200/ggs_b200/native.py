@@ -38,6 +38,8 @@ SIGNATURES = {
     "ggs_ctx_set_target": (_i, [_vp, _vp, _vp, _i, _i]),
     "ggs_ctx_fitness_host": (_i, [_vp, _vp, _i, _i, _i, _i, _f, _i, _f, _vp]),
     "ggs_probe_peaks": (_i, [ctypes.POINTER(_f)]),
+    "ggs_ga_breed": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _f, _f, ctypes.POINTER(_f), _f, _f,
+                          ctypes.c_uint64, ctypes.c_uint32, _vp]),
     "ggs_stats_target": (_i, [_vp]),
     "ggs_timing_enable": (_i, [_i]),
     "ggs_timing_read": (_i, [ctypes.POINTER(_f), ctypes.POINTER(_f), ctypes.POINTER(_i)]),

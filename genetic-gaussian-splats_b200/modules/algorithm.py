@@ -1,7 +1,7 @@
 """Genetic-algorithm loop (reference: modules/algorithm.py:17-195), same entry point and
 return value, restructured around a population tensor that stays resident on the device:
-selection, crossover, mutation and elitism are batched tensor ops (modules/genetic.py), the
-evaluation is the fused CUDA path, and the only host transfer per generation is the fitness
+selection, crossover and mutation are one CUDA launch (ggs_ga_breed via modules/genetic.py),
+elitism is a row copy, the evaluation is the fused CUDA path, and the only host transfer per generation is the fitness
 vector.  Two reference quirks are dropped because they cannot change results: elites are not
 re-evaluated (the evaluation is deterministic, algorithm.py:134) -- their stored fitness is
 reused -- and the offspring that elitism would discard are still evaluated (one launch)."""
@@ -18,7 +18,7 @@ except Exception:  # tqdm is optional
         return it
 
 from modules.fitness import fitness_many
-from modules.genetic import crossover_population, mutate_population, tournament_indices
+from modules.genetic import breed_population
 from modules.mask import compute_importance_mask
 from modules.population import new_population
 from modules.utils import (_anneal_factor, prewarm_renderer, save_curves_csv, save_frame_png,
@@ -75,15 +75,14 @@ def genetic_approx(target_img_uint8: torch.Tensor,
         save_frame_png(0, best_ind, pad, prefix, video_dir, H, W, k_sigma, device, save_video)
 
     n_elite = max(1, elite_k)
+    run_seed = int(torch.randint(0, 2**31 - 1, (1,)).item())  # follows torch.manual_seed
     pbar = tqdm(range(1, generations + 1), desc="GA generations", leave=True)
     try:
         for gen in pbar:
-            # selection -> shuffle -> crossover -> mutation, all on the resident tensor
-            parents = pop[tournament_indices(fit, pop_size, k=tour_k)]
-            parents = parents[torch.randperm(pop_size, device=pop.device)]
-            offspring = crossover_population(parents, cxpb)
-            mutate_population(offspring, gen, generations, schedule, mut_sigma_max, mut_sigma_min,
-                              mutpb, H, W, min_scale_splats, max_scale_splats)
+            # selection -> crossover -> mutation: one launch on the resident tensor
+            offspring = breed_population(pop, fit, gen, generations, schedule, mut_sigma_max,
+                                         mut_sigma_min, tour_k, cxpb, mutpb, H, W,
+                                         min_scale_splats, max_scale_splats, seed=run_seed)
             off_fit = evaluate(offspring)
 
             # elitism: the n_elite best of the current generation survive unchanged

@@ -52,6 +52,31 @@ def mutate_individual(ind: torch.Tensor, is_elite: bool, gen: int, total_gens: i
 # ----------------------------------------------------------------------------- batched, on device
 
 @torch.no_grad()
+def breed_population(pop: torch.Tensor, fitness: torch.Tensor, gen: int, total_gens: int,
+                     schedule: str, mut_sigma_max: dict, mut_sigma_min: dict, tour_k: int,
+                     cxpb: float, mutpb: float, H: int, W: int, min_scale_splats: float,
+                     max_scale_splats: float, seed: int = 0) -> torch.Tensor:
+    """Selection + crossover + mutation of the whole population -> offspring [P,N,9].
+
+    On a CUDA population this is ONE kernel launch (ggs_ga_breed in libggs_b200.so, Philox
+    counter-based randomness keyed by (seed, gen)); on a CPU population (tests) it is the
+    composition of the batched torch operators below.  Same operators either way."""
+    from modules.utils import scale_log_bounds
+    if pop.is_cuda:
+        from ggs_b200 import breed
+        lo, hi = scale_log_bounds(H, W, min_scale_splats, max_scale_splats)
+        sigma = build_mut_sigma(gen, total_gens, schedule, mut_sigma_max, mut_sigma_min)
+        return breed(pop, fitness, sigma, tour_k=tour_k, cxpb=cxpb, mutpb=mutpb, log_scale_lo=lo,
+                     log_scale_hi=hi, seed=seed, generation=gen)
+    P = pop.shape[0]
+    parents = pop[tournament_indices(fitness, P, k=tour_k)]
+    parents = parents[torch.randperm(P, device=pop.device)]
+    offspring = crossover_population(parents[..., :9].contiguous(), cxpb)
+    return mutate_population(offspring, gen, total_gens, schedule, mut_sigma_max, mut_sigma_min,
+                             mutpb, H, W, min_scale_splats, max_scale_splats)
+
+
+@torch.no_grad()
 def tournament_indices(fitness: torch.Tensor, n_parents: int, k: int = 2,
                        generator=None) -> torch.Tensor:
     """[n_parents] indices: each the best of k uniform draws (genetic.py:8-14, batched)."""

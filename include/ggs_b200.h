@@ -133,6 +133,26 @@ int ggs_ctx_set_target(ggs_ctx *ctx, const float *h_target, const float *h_mask,
 int ggs_ctx_fitness_host(ggs_ctx *ctx, const float *h_genomes, int layout, int B, int N,
                          int cols, float k_sigma, int mode, float boost_beta, float *h_fitness);
 
+/* ---- GA breeding step (callers of the hot path; SURVEY.md section 8f "next" #1) ---- */
+
+/*
+ * One generation of selection + crossover + mutation for the whole population in one launch:
+ * tournament_selection (modules/genetic.py:8-14) with the shuffle/pairing of
+ * algorithm.py:87-100, crossover_uniform (genetic.py:17-21), mutate_individual
+ * (genetic.py:32-92, incl. the "at least one gene per group" rule and the size-ordered splat
+ * swap) and clamp_genome (utils.py:36-45).
+ * d_population: [P][N][cols] axes-angle genomes; d_fitness: [P] (lower is better);
+ * d_offspring: [P][N][9], must not alias the population (elitism is the caller's row copy).
+ * h_sigma6: annealed mutation sigmas on the host, in the order xy, alog, blog, theta, rgb,
+ * alpha (build_mut_sigma, utils.py:31-33); log_scale_lo/hi: log of the legal sigma range.
+ * Counter-based RNG: the result is a pure function of (seed, generation, inputs).  Same
+ * distributions as the reference, different random streams.
+ */
+int ggs_ga_breed(const float *d_population, const float *d_fitness, int P, int N, int cols,
+                 float *d_offspring, int tour_k, float cxpb, float mutpb, const float *h_sigma6,
+                 float log_scale_lo, float log_scale_hi, uint64_t seed, uint32_t generation,
+                 void *stream);
+
 /* ---- hardware probes used by bench.py for the roofline denominators -------------- */
 
 /*

@@ -1,0 +1,186 @@
+"""GPU tests of the one-launch GA breeding step (ggs_ga_breed): the operators must draw from
+the reference's distributions (genetic.py:8-92, utils.py:36-45); the streams differ."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+SIG = {"xy": 0.05, "alog": 0.3, "blog": 0.2, "theta": 0.1, "rgb": 10.0, "alpha": 5.0}
+ZERO = {k: 0.0 for k in SIG}
+
+
+@pytest.fixture(scope="module")
+def ggs():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import ggs_b200
+    ggs_b200.lib()
+    return ggs_b200
+
+
+def hidden_target(H, W, n, seed=7):
+    from modules.encode import genome_to_renderer_batched
+    from modules.population import new_population
+    from modules.render import render_splats_rgb_triton
+    torch.manual_seed(seed)
+    g = new_population(1, n, H, W, 3.0, 0.1, device="cuda")
+    return render_splats_rgb_triton(genome_to_renderer_batched(g), H, W, k_sigma=3.0, device="cuda")[0].cpu()
+
+
+def population(P, N, H=128, W=128, seed=0):
+    from ggs_b200 import synth
+    g = synth.new_population_np(P, N, H, W, seed=seed)
+    g[..., 0:2] = 0.25 + 0.5 * g[..., 0:2]          # keep clear of the clamp bounds
+    g[..., 5:9] = 60.0 + 0.5 * g[..., 5:9]
+    return torch.from_numpy(g).cuda()
+
+
+LO, HI = math.log(3.0), math.log(12.8)
+
+
+def breed(ggs, pop, fit, sigma=SIG, **kw):
+    args = dict(tour_k=2, cxpb=0.0, mutpb=0.05, log_scale_lo=LO, log_scale_hi=HI, seed=1234,
+                generation=7)
+    args.update(kw)
+    return ggs.breed(pop, fit, sigma, **args)
+
+
+def test_reproducible_and_seed_sensitive(ggs):
+    pop = population(32, 100)
+    fit = torch.rand(32, device="cuda")
+    a = breed(ggs, pop, fit)
+    assert a.shape == (32, 100, 9) and torch.isfinite(a).all()
+    assert torch.equal(a, breed(ggs, pop, fit))
+    assert not torch.equal(a, breed(ggs, pop, fit, seed=1235))
+    assert not torch.equal(a, breed(ggs, pop, fit, generation=8))
+
+
+def test_no_mutation_noise_children_are_parent_rows(ggs):
+    # sigma = 0, no crossover: every child is a copy of a parent up to one row swap
+    P, N = 64, 50
+    pop = population(P, N)
+    fit = torch.rand(P, device="cuda")
+    off = breed(ggs, pop, fit, sigma=ZERO)
+    popn, offn = pop.cpu().numpy(), off.cpu().numpy()
+    for c in range(P):
+        srt = np.sort(offn[c].round(4), axis=0)
+        ok = any(np.allclose(srt, np.sort(popn[p].round(4), axis=0), atol=2e-4) for p in range(P))
+        assert ok, c
+        # at most two rows differ from the parent that matches on most rows (the swap)
+        best = max(range(P), key=lambda p: (np.abs(popn[p] - offn[c]).max(axis=1) < 1e-3).sum())
+        moved = (np.abs(popn[best] - offn[c]).max(axis=1) >= 1e-3).nonzero()[0]
+        assert len(moved) in (0, 2)
+        if len(moved) == 2:
+            i, j = moved
+            size = offn[c][:, 2] + offn[c][:, 3]
+            assert size[i] > size[j]               # the bigger splat moved to the earlier slot
+
+
+def test_tournament_prefers_low_fitness(ggs):
+    P, N = 256, 8
+    pop = population(P, N)
+    pop[:, :, 5] = torch.arange(P, device="cuda", dtype=torch.float32)[:, None] / 2.0 + 60.0  # tag = index
+    fit = torch.arange(P, device="cuda", dtype=torch.float32)
+    off = breed(ggs, pop, fit, sigma=ZERO, mutpb=0.0)
+    parent = ((off[:, 0, 5] - 60.0) * 2.0).round()
+    # expected index of the best of two uniform draws is ~P/3, far below the mean P/2
+    assert parent.mean().item() < 0.42 * P
+    off4 = breed(ggs, pop, fit, sigma=ZERO, mutpb=0.0, tour_k=6)
+    assert ((off4[:, 0, 5] - 60.0) * 2.0).mean().item() < parent.mean().item()
+
+
+def test_crossover_exchanges_whole_rows_between_the_pair(ggs):
+    P, N = 40, 64
+    pop = population(P, N)
+    fit = torch.rand(P, device="cuda")
+    off = breed(ggs, pop, fit, sigma=ZERO, mutpb=0.0, cxpb=1.0).cpu().numpy()
+    popn = pop.cpu().numpy()
+    for pair in range(P // 2):
+        c1, c2 = off[2 * pair], off[2 * pair + 1]
+        both = np.sort(np.concatenate([c1, c2]).round(4), axis=0)
+        found = False
+        for a in range(P):
+            for b in range(P):
+                if np.allclose(both, np.sort(np.concatenate([popn[a], popn[b]]).round(4), axis=0), atol=2e-4):
+                    found = True
+                    break
+            if found:
+                break
+        assert found, pair
+
+
+def test_mutation_statistics(ggs):
+    # rates ~ mutpb per gene group, noise std ~ sigma (measured on unclamped genes)
+    P, N = 256, 400
+    pop = population(P, N)
+    pop[..., 2:4] = 0.5 * (LO + HI)
+    pop[..., 4] = 0.0
+    pop = pop[0:1].repeat(P, 1, 1).contiguous()     # identical parents: selection cannot matter
+    fit = torch.rand(P, device="cuda")
+    off = breed(ggs, pop, fit, mutpb=0.05)
+    src = pop[0].unsqueeze(0)
+    # undo the row swap by comparing sorted-on-colour is fragile: instead use rows that did not move
+    d = (off - src)
+    stayed = ((d != 0).sum(dim=-1) <= 5).unsqueeze(-1).expand_as(d)  # a swapped row differs in x, y, r, g, b, alpha
+    for col, key, rate_cols in ((0, "xy", 1), (2, "alog", 1), (3, "blog", 1), (4, "theta", 1), (8, "alpha", 1)):
+        x = d[..., col][stayed[..., col]]
+        changed = x != 0
+        rate = changed.float().mean().item()
+        assert 0.035 < rate < 0.065, (key, rate)
+        std = x[changed].std().item()
+        assert abs(std / SIG[key] - 1.0) < 0.08, (key, std)
+    rgb = d[..., 5:8][stayed[..., 0]]
+    moved = rgb != 0
+    # one flag drives the three colour channels together
+    assert (moved.all(dim=-1) | (~moved).all(dim=-1)).float().mean().item() > 0.999
+    assert abs(rgb[moved].std().item() / SIG["rgb"] - 1.0) < 0.08
+
+
+def test_at_least_one_gene_per_group_and_projection(ggs):
+    # mutpb = 0: exactly the forced genes mutate; all outputs stay inside the legal box
+    P, N = 128, 20
+    pop = population(P, N)
+    fit = torch.rand(P, device="cuda")
+    big = {k: 10.0 * v for k, v in SIG.items()}
+    off = breed(ggs, pop, fit, sigma=big, mutpb=0.0)
+    assert off[..., 0:2].min() >= 0 and off[..., 0:2].max() <= 1
+    assert off[..., 2:4].min() >= LO - 1e-6 and off[..., 2:4].max() <= HI + 1e-6
+    assert off[..., 4].abs().max() <= math.pi + 1e-5
+    assert off[..., 5:9].min() >= 0 and off[..., 5:9].max() <= 255
+
+    src = breed(ggs, pop, fit, sigma=ZERO, mutpb=0.0)       # same selection and swap, no noise
+    # (a) noise on everything but the scales: sizes, hence the swap, are unchanged, so rows line
+    #     up and exactly the forced genes differ: xy 1 + theta 1 + colour (rgb 3 | alpha 1)
+    no_ab = dict(big, alog=0.0, blog=0.0)
+    off_a = breed(ggs, pop, fit, sigma=no_ab, mutpb=0.0)
+    per_child = ((off_a - src).abs() > 1e-6).reshape(P, -1).sum(dim=1)
+    assert per_child.max().item() <= 5 and per_child.float().mean().item() > 2.5
+    # (b) noise on the scales only: match rows through the untouched x coordinate
+    only_ab = dict(ZERO, alog=0.4, blog=0.4)
+    off_b = breed(ggs, pop, fit, sigma=only_ab, mutpb=0.0)
+    ia, ib = off_b[..., 0].argsort(dim=1), src[..., 0].argsort(dim=1)
+    sb = torch.gather(off_b[..., 2:4], 1, ia.unsqueeze(-1).expand(-1, -1, 2))
+    ss = torch.gather(src[..., 2:4], 1, ib.unsqueeze(-1).expand(-1, -1, 2))
+    changed = ((sb - ss).abs() > 1e-6).reshape(P, -1).sum(dim=1)
+    assert changed.max().item() <= 1 and changed.float().mean().item() > 0.8
+
+
+def test_ga_loop_uses_the_kernel_and_improves(ggs):
+    import modules.config as C
+    from modules.algorithm import genetic_approx
+    H = W = 64
+    target = hidden_target(H, W, 40)
+    kw = dict(pop_size=33, n_splats=40, tour_k=2, elite_k=4, cxpb=0.05, mutpb=0.05,
+              mut_sigma_max=C.MUT_SIGMA_MAX, mut_sigma_min=C.MUT_SIGMA_MIN, schedule="cosine",
+              min_scale_splats=3.0, max_scale_splats=0.1, k_sigma=3.0, mask_strength=0.7,
+              boost_only=False)
+    torch.manual_seed(0)
+    _, f0 = genetic_approx(target, H, W, "cuda", generations=0, **kw)
+    torch.manual_seed(0)
+    _, f1 = genetic_approx(target, H, W, "cuda", generations=80, **kw)
+    torch.manual_seed(0)
+    _, f2 = genetic_approx(target, H, W, "cuda", generations=80, **kw)
+    assert f1 < 0.9 * f0 and f1 == f2              # improves, and reproducible for a fixed seed
