@@ -111,3 +111,18 @@ def test_temperature_schedule():
     assert _temp_schedule("linear", 1.0, 100, 100) == 1e-12
     assert abs(_temp_schedule("exp", 1.0, 100, 100) - 0.01) < 1e-9
     assert _temp_schedule("cauchy", 1.0, 9, 100) == 0.1
+
+
+def test_breed_population_cpu_path_keeps_shape_and_box():
+    # on CPU tensors breed_population composes the batched torch operators (the CUDA launch
+    # needs a device); same contract: [P,N,9] legal genomes
+    torch.manual_seed(2)
+    pop = P.new_population(10, 30, 64, 64, 3.0, 0.1, device="cpu")
+    fit = torch.rand(10)
+    off = G.breed_population(pop, fit, 3, 50, "cosine", C.MUT_SIGMA_MAX, C.MUT_SIGMA_MIN, 2, 0.5,
+                             0.05, 64, 64, 3.0, 0.1)
+    lo, hi = U.scale_log_bounds(64, 64, 3.0, 0.1)
+    assert off.shape == (10, 30, 9) and off.data_ptr() != pop.data_ptr()
+    assert off[..., :2].min() >= 0 and off[..., :2].max() <= 1
+    assert off[..., 2:4].min() >= lo - 1e-6 and off[..., 2:4].max() <= hi + 1e-6
+    assert off[..., 5:9].min() >= 0 and off[..., 5:9].max() <= 255
