@@ -372,3 +372,67 @@ def test_full_size_config3_properties(ggs):
     tot = f.double().mean().item()
     parts = 0.5 * (f[:512].double().mean().item() + f[512:].double().mean().item())
     assert abs(tot - parts) <= 1e-12 * max(1.0, abs(tot))
+
+
+# ------------------------------------------------------------- plumbing: streams, graphs, cols
+
+def test_wide_genome_rows_take_the_unstaged_decode_path(ggs):
+    # cols > 16 bypasses the shared-memory staging of the decode kernel
+    from ggs_b200 import synth
+    B, N, H, W = 3, 70, 64, 96
+    g9 = synth.new_population_np(B, N, H, W, seed=31)
+    g24 = np.concatenate([g9, np.random.default_rng(0).normal(size=(B, N, 15)).astype(np.float32)], axis=-1)
+    t = synth.synthetic_target_np(H, W, 31)
+    a = ggs.fitness(cuda(g9), cuda(t), H, W, 3.0)
+    b = ggs.fitness(cuda(g24), cuda(t), H, W, 3.0)
+    assert torch.equal(a, b)
+    assert torch.equal(ggs.encode(cuda(g24)), ggs.encode(cuda(g9)))
+
+
+def test_non_default_stream_and_noncontiguous_input(ggs):
+    from ggs_b200 import synth
+    B, N, H, W = 16, 120, 96, 96
+    g = cuda(synth.new_population_np(B, N, H, W, seed=32))
+    t = cuda(synth.synthetic_target_np(H, W, 32))
+    ref = ggs.fitness(g, t, H, W, 3.0)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        on_side = ggs.fitness(g, t, H, W, 3.0)
+    s.synchronize()
+    assert torch.equal(on_side, ref)
+    padded = torch.zeros((B, N, 12), device="cuda")
+    padded[..., :9] = g
+    view = padded[..., :9]                      # non-contiguous view, made contiguous inside
+    assert not view.is_contiguous()
+    assert torch.equal(ggs.fitness(view, t, H, W, 3.0), ref)
+    assert torch.equal(ggs.fitness(g.double(), t, H, W, 3.0), ref)   # dtype is converted like the reference
+
+
+def test_cuda_graph_capture_and_replay(ggs):
+    # the device-pointer entries only enqueue work on the caller's stream and never allocate,
+    # so an evaluation can be captured once and replayed (the SA inner loop)
+    from ggs_b200 import synth
+    B, N, H, W = 8, 200, 128, 128
+    g = cuda(synth.new_population_np(B, N, H, W, seed=33))
+    g2 = cuda(synth.new_population_np(B, N, H, W, seed=34))
+    t = cuda(synth.synthetic_target_np(H, W, 33))
+    m = cuda(synth.importance_mask_np(synth.synthetic_target_np(H, W, 33)))
+    eager1 = ggs.fitness(g, t, H, W, 3.0, weight_mask=m)
+    eager2 = ggs.fitness(g2, t, H, W, 3.0, weight_mask=m)
+    static_g = g.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ggs.fitness(static_g, t, H, W, 3.0, weight_mask=m)     # warm-up on the capture stream
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        static_out = ggs.fitness(static_g, t, H, W, 3.0, weight_mask=m)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, eager1)
+    static_g.copy_(g2)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, eager2)
