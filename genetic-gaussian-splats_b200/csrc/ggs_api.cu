@@ -112,8 +112,8 @@ static cudaEvent_t *timing_slot()
 // decode + raster on `stream`; the one launch sequence behind every public entry.
 static int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
                     float k_sigma, const float bg[3], const float *d_target, const float *d_mask,
-                    int mode, float beta, float *d_fitness, float *d_images, void *d_workspace,
-                    size_t workspace_bytes_given, cudaStream_t stream)
+                    int mode, float beta, float *d_fitness, void *d_images, int image_u8,
+                    void *d_workspace, size_t workspace_bytes_given, cudaStream_t stream)
 {
     if (B == 0) return GGS_OK;
     if (d_genomes == nullptr && N > 0) {
@@ -136,7 +136,7 @@ static int evaluate(const float *d_genomes, int layout, int B, int N, int cols, 
                            nullptr, nullptr, ws.counter, B, stream));
     if (ev) GGS_CUDA(cudaEventRecord(ev[1], stream));
     GGS_CUDA(launch_raster(ws, B, N, H, W, bg, d_target, d_mask, mode, beta, d_fitness, d_images,
-                           g_stats, stream));
+                           image_u8, g_stats, stream));
     if (ev) GGS_CUDA(cudaEventRecord(ev[2], stream));
     return GGS_OK;
 }
@@ -206,8 +206,27 @@ int ggs_render(const float *d_genomes, int layout, int B, int N, int cols, int H
     const float white[3] = {1.0f, 1.0f, 1.0f};
     const float *bg = h_background ? h_background : white;
     return evaluate(d_genomes, layout, B, N, cols, H, W, k_sigma, bg, nullptr, nullptr,
-                    GGS_MODE_PLAIN, 1.0f, nullptr, d_images, d_workspace, workspace_bytes_given,
+                    GGS_MODE_PLAIN, 1.0f, nullptr, d_images, 0, d_workspace, workspace_bytes_given,
                     static_cast<cudaStream_t>(stream));
+}
+
+int ggs_render_u8(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
+                  float k_sigma, const float *h_background, unsigned char *d_images_u8,
+                  void *d_workspace, size_t workspace_bytes_given, void *stream)
+{
+    int rc = check_layout(layout);
+    if (rc) return rc;
+    rc = check_shape(B, N, cols, H, W);
+    if (rc) return rc;
+    if (B > 0 && d_images_u8 == nullptr) {
+        set_error("ggs_render_u8: d_images_u8 is NULL");
+        return GGS_EINVAL;
+    }
+    const float white[3] = {1.0f, 1.0f, 1.0f};
+    const float *bg = h_background ? h_background : white;
+    return evaluate(d_genomes, layout, B, N, cols, H, W, k_sigma, bg, nullptr, nullptr,
+                    GGS_MODE_PLAIN, 1.0f, nullptr, d_images_u8, 1, d_workspace,
+                    workspace_bytes_given, static_cast<cudaStream_t>(stream));
 }
 
 int ggs_fitness(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
@@ -233,7 +252,7 @@ int ggs_fitness(const float *d_genomes, int layout, int B, int N, int cols, int 
     }
     const float white[3] = {1.0f, 1.0f, 1.0f};  // render.py:209
     return evaluate(d_genomes, layout, B, N, cols, H, W, k_sigma, white, d_target, d_mask, mode,
-                    boost_beta, d_fitness, d_images, d_workspace, workspace_bytes_given,
+                    boost_beta, d_fitness, d_images, 0, d_workspace, workspace_bytes_given,
                     static_cast<cudaStream_t>(stream));
 }
 
@@ -383,7 +402,7 @@ int ggs_ctx_fitness_host(ggs_ctx *c, const float *h_genomes, int layout, int B, 
         GGS_CUDA(cudaMemcpyAsync(c->d_genomes[s], h_genomes + (size_t)b0 * N * cols, sb * row_bytes,
                                  cudaMemcpyHostToDevice, c->stream[s]));
         rc = evaluate(c->d_genomes[s], layout, sb, N, cols, c->H, c->W, k_sigma, white, c->d_target,
-                      c->d_mask, mode, boost_beta, c->d_fitness + b0, nullptr, c->d_ws[s],
+                      c->d_mask, mode, boost_beta, c->d_fitness + b0, nullptr, 0, c->d_ws[s],
                       c->ws_cap[s], c->stream[s]);
         if (rc) return rc;
     }

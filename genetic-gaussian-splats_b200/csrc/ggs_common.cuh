@@ -60,8 +60,8 @@ cudaError_t launch_encode(const float *d_axes, int64_t rows, int cols, float *d_
 // raster.cu
 cudaError_t launch_raster(const Workspace &ws, int B, int N, int H, int W, const float bg[3],
                           const float *d_target, const float *d_mask, int mode, float beta,
-                          float *d_fitness, float *d_images, unsigned long long *d_stats,
-                          cudaStream_t stream);
+                          float *d_fitness, void *d_images, int image_u8,
+                          unsigned long long *d_stats, cudaStream_t stream);
 
 // breed.cu
 cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int N, int cols,

@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS)
 raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, int N, int H, int W,
               int ntx, int ntiles, float bg_r, float bg_g, float bg_b,
               const float *__restrict__ target, const float *__restrict__ mask, int mode,
-              float beta, float *__restrict__ images, float2 *__restrict__ partial,
+              float beta, float *__restrict__ images, int image_u8, float2 *__restrict__ partial,
               int *__restrict__ counter, float *__restrict__ fitness,
               unsigned long long *__restrict__ stats)
 {
@@ -390,10 +390,18 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
             const float cb = clamp01(fmaf(tr, bg_b, pb[i & 1]));
             const int64_t p = (int64_t)Y * W + X;
             if (images != nullptr) {
-                float *o = images + ((int64_t)b * H * W + p) * 3;
-                o[0] = cr;
-                o[1] = cg;
-                o[2] = cb;
+                const int64_t at = ((int64_t)b * H * W + p) * 3;
+                if (image_u8) {  // (img * 255).astype(uint8): truncation (utils.py:57)
+                    unsigned char *o = reinterpret_cast<unsigned char *>(images) + at;
+                    o[0] = (unsigned char)(cr * 255.0f);
+                    o[1] = (unsigned char)(cg * 255.0f);
+                    o[2] = (unsigned char)(cb * 255.0f);
+                } else {
+                    float *o = images + at;
+                    o[0] = cr;
+                    o[1] = cg;
+                    o[2] = cb;
+                }
             }
             if (want_fit) {
                 const float dr = cr - __ldg(target + 3 * p + 0);
@@ -472,8 +480,8 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
 
 cudaError_t launch_raster(const Workspace &ws, int B, int N, int H, int W, const float bg[3],
                           const float *d_target, const float *d_mask, int mode, float beta,
-                          float *d_fitness, float *d_images, unsigned long long *d_stats,
-                          cudaStream_t stream)
+                          float *d_fitness, void *d_images, int image_u8,
+                          unsigned long long *d_stats, cudaStream_t stream)
 {
     if (B <= 0) return cudaSuccess;
     const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
@@ -482,11 +490,13 @@ cudaError_t launch_raster(const Workspace &ws, int B, int N, int H, int W, const
     if (d_stats != nullptr)
         raster_kernel<true><<<(unsigned)grid, kThreads, 0, stream>>>(
             ws.rec, ws.aabb, N, H, W, ntx, ntiles, bg[0], bg[1], bg[2], d_target, d_mask, mode,
-            beta, d_images, ws.partial, ws.counter, d_fitness, d_stats);
+            beta, static_cast<float *>(d_images), image_u8, ws.partial, ws.counter, d_fitness,
+            d_stats);
     else
         raster_kernel<false><<<(unsigned)grid, kThreads, 0, stream>>>(
             ws.rec, ws.aabb, N, H, W, ntx, ntiles, bg[0], bg[1], bg[2], d_target, d_mask, mode,
-            beta, d_images, ws.partial, ws.counter, d_fitness, nullptr);
+            beta, static_cast<float *>(d_images), image_u8, ws.partial, ws.counter, d_fitness,
+            nullptr);
     return cudaGetLastError();
 }
 

@@ -95,20 +95,22 @@ def decode(genomes: torch.Tensor, H: int, W: int, k_sigma: float = 3.0,
 
 @torch.no_grad()
 def render(genomes: torch.Tensor, H: int, W: int, k_sigma: float = 3.0,
-           background=(1.0, 1.0, 1.0), layout: int = LAYOUT_CHOLESKY, device=None) -> torch.Tensor:
-    """[B,N,C>=9] genomes -> [B,H,W,3] float32 in [0,1] (render.py:204-252)."""
+           background=(1.0, 1.0, 1.0), layout: int = LAYOUT_CHOLESKY, device=None,
+           as_uint8: bool = False) -> torch.Tensor:
+    """[B,N,C>=9] genomes -> [B,H,W,3] float32 in [0,1] (render.py:204-252), or uint8
+    (image * 255 truncated, utils.py:57) when as_uint8."""
     dev = _cuda_device(device if device is not None else genomes.device)
     g = _as_f32(genomes, dev)
     assert g.ndim == 3 and g.shape[2] >= 9
     B, N, C = g.shape
-    img = torch.empty((B, H, W, 3), dtype=torch.float32, device=dev)
+    img = torch.empty((B, H, W, 3), dtype=torch.uint8 if as_uint8 else torch.float32, device=dev)
     bg = (ctypes.c_float * 3)(*[float(v) for v in background])
     nbytes = lib().ggs_workspace_bytes(B, N, int(H), int(W))
+    entry = lib().ggs_render_u8 if as_uint8 else lib().ggs_render
     with torch.cuda.device(dev):
         ws = _workspace(dev, nbytes)
-        check(lib().ggs_render(g.data_ptr(), layout, B, N, C, int(H), int(W), float(k_sigma), bg,
-                               img.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)),
-              "ggs_render")
+        check(entry(g.data_ptr(), layout, B, N, C, int(H), int(W), float(k_sigma), bg,
+                    img.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "ggs_render")
     return img
 
 

@@ -31,6 +31,7 @@ SIGNATURES = {
     "ggs_encode": (_i, [_vp, _i64, _i, _vp, _vp]),
     "ggs_decode": (_i, [_vp, _i, _i64, _i, _i, _i, _f, _vp, _vp, _vp]),
     "ggs_render": (_i, [_vp, _i, _i, _i, _i, _i, _i, _f, ctypes.POINTER(_f), _vp, _vp, _sz, _vp]),
+    "ggs_render_u8": (_i, [_vp, _i, _i, _i, _i, _i, _i, _f, ctypes.POINTER(_f), _vp, _vp, _sz, _vp]),
     "ggs_fitness": (_i, [_vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz,
                          _vp]),
     "ggs_ctx_create": (_i, [_i, ctypes.POINTER(_vp)]),

@@ -53,12 +53,13 @@ def clamp_genome(ind: torch.Tensor, H: int, W: int, min_scale_splats: float,
 def render_axes_angle_to_img(ind_axes_angle: torch.Tensor, Hsnap: int, Wsnap: int,
                              k_sigma: float, device) -> np.ndarray:
     """One individual -> uint8 [H,W,3]."""
-    from modules.encode import genome_to_renderer_batched
-    from modules.render import render_splats_rgb_triton
+    from ggs_b200 import LAYOUT_AXES_ANGLE, render
     G = ind_axes_angle.unsqueeze(0) if ind_axes_angle.ndim == 2 else ind_axes_angle
-    G9 = genome_to_renderer_batched(G.to(device))
-    img = render_splats_rgb_triton(G9, Hsnap, Wsnap, k_sigma=k_sigma, device=device, tile=32)[0]
-    return (img.clamp(0, 1).detach().cpu().numpy() * 255.0).astype("uint8")
+    # encode + decode + render + the (img * 255).astype(uint8) conversion in one evaluation on
+    # the device; only H*W*3 bytes come back
+    img8 = render(G, int(Hsnap), int(Wsnap), k_sigma=float(k_sigma), layout=LAYOUT_AXES_ANGLE,
+                  device=device, as_uint8=True)[0]
+    return img8.cpu().numpy()
 
 
 @torch.no_grad()

@@ -94,6 +94,16 @@ int ggs_render(const float *d_genomes, int layout, int B, int N, int cols, int H
                size_t workspace_bytes, void *stream);
 
 /*
+ * Same render, 8-bit output for frames and final images: d_images_u8 [B][H][W][3] =
+ * (uint8)(image * 255), truncating like the reference's
+ * (img.clamp(0,1).cpu().numpy() * 255).astype("uint8")  (modules/utils.py:57, run_ggs.py:71);
+ * a quarter of the bytes cross PCIe.
+ */
+int ggs_render_u8(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
+                  float k_sigma, const float *h_background, unsigned char *d_images_u8,
+                  void *d_workspace, size_t workspace_bytes, void *stream);
+
+/*
  * fitness_many (modules/fitness.py:8-31): encode + decode + render + masked squared
  * error fused; candidate images never touch HBM unless d_images is given.
  * d_genomes: [B][N][cols] in `layout` (the reference passes axes-angle);

@@ -436,3 +436,20 @@ def test_cuda_graph_capture_and_replay(ggs):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(static_out, eager2)
+
+
+def test_uint8_frames_match_the_reference_conversion(ggs, golden):
+    # utils.py:49-58: (img.clamp(0,1).cpu().numpy() * 255).astype("uint8"), done on device
+    from modules.utils import render_axes_angle_to_img
+    H, W, k = int(golden["H"]), int(golden["W"]), float(golden["k_sigma"])
+    chol = cuda(golden["chol"])
+    f32 = ggs.render(chol, H, W, k)
+    u8 = ggs.render(chol, H, W, k, as_uint8=True)
+    assert u8.dtype == torch.uint8 and u8.shape == f32.shape
+    expect = (f32.cpu().numpy() * 255.0).astype("uint8")
+    assert np.array_equal(u8.cpu().numpy(), expect)
+    ref8 = (golden["images"] * 255.0).astype("uint8").astype(np.int16)
+    assert np.abs(u8.cpu().numpy().astype(np.int16) - ref8).max() <= 1   # 1e-4 can cross a step
+    frame = render_axes_angle_to_img(cuda(golden["axes"])[0], H, W, k, "cuda")
+    assert frame.dtype == np.uint8 and frame.shape == (H, W, 3)
+    assert np.abs(frame.astype(np.int16) - ref8[0]).max() <= 1
