@@ -115,3 +115,30 @@ def test_mask_matches_reference_formula_on_fixture(golden):
     from ggs_b200 import synth
     m = synth.importance_mask_np(golden["target"], strength=0.7)
     np.testing.assert_allclose(m, golden["mask"], atol=1e-6)
+
+
+def test_run_scripts_can_import_everything_they_need():
+    # run_ggs.py:8-12 and run_sags.py:8-12 import these names and call the loops by keyword
+    import inspect
+    from modules.algorithm import genetic_approx
+    from modules.annealing import simulated_annealing
+    from modules.config import (BOOST_ONLY, CXPB, DEFAULT_TILE_SIZE, ELITE_K, FRAME_EVERY, GENERATIONS,  # noqa: F401
+                                INPUT_DIR, K_SIGMA, LOSS_LOG_Y, MASK_STRENGTH, MAX_SCALE_SPLATS,
+                                MIN_SCALE_SPLATS, MUT_SIGMA_MAX, MUT_SIGMA_MIN, MUTPB, N_SPLATS,
+                                OUTPUT_DIR, POP_SIZE, REF_IMG, SA_SCHEDULE, SA_T0, SA_TRIES_PER_ITER,
+                                SAVE_LOSS_CURVE, SAVE_VIDEO, SCHEDULE, SEED, TOUR_K, WORK_MAX_SIDE)
+    from modules.encode import genome_to_renderer  # noqa: F401
+    from modules.render import _DEV, render_splats_rgb_triton  # noqa: F401
+    from modules.resize import choose_work_size, scale_genome_pixels_anisotropic  # noqa: F401
+    ga = list(inspect.signature(genetic_approx).parameters)
+    assert ga == ["target_img_uint8", "H", "W", "device", "pop_size", "n_splats", "generations",
+                  "tour_k", "elite_k", "cxpb", "mutpb", "mut_sigma_max", "mut_sigma_min", "schedule",
+                  "min_scale_splats", "max_scale_splats", "k_sigma", "mask_strength", "boost_only",
+                  "save_video", "frame_every", "video_dir", "prefix", "loss_png_path",
+                  "loss_csv_path", "loss_log_y"]
+    sa = list(inspect.signature(simulated_annealing).parameters)
+    assert sa[:26] == ["target_img_uint8", "H", "W", "device", "n_splats", "mutpb", "mut_sigma_max",
+                       "mut_sigma_min", "sigma_schedule", "min_scale_splats", "max_scale_splats",
+                       "k_sigma", "mask_strength", "boost_only", "iterations", "temp0",
+                       "temp_schedule", "tries_per_iter", "save_video", "frame_every", "video_dir",
+                       "prefix", "loss_png_path", "loss_csv_path", "loss_log_y", "batch_neighbors"]

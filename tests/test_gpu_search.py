@@ -115,3 +115,41 @@ def test_two_gpu_nccl_gather_is_bit_identical(cuda_ok, tmp_path):
            "--master-addr", "127.0.0.1", "--master-port", "29653", str(script), ROOT]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_run_ggs_flow_end_to_end(cuda_ok, tmp_path):
+    """The flow of run_ggs.py:31-77 with its outputs: load an image file, choose the work size,
+    run the GA with frames and loss curves, rescale the best genome and render it at full size."""
+    import modules.config as C
+    from PIL import Image
+    from modules.algorithm import genetic_approx
+    from modules.encode import genome_to_renderer
+    from modules.render import _DEV as DEV, render_splats_rgb_triton
+    from modules.resize import choose_work_size, scale_genome_pixels_anisotropic
+    H_out, W_out = 96, 144
+    src = (hidden_target(H_out, W_out, 60).numpy() * 255).astype("uint8")
+    img_path = tmp_path / "reference.jpg"
+    Image.fromarray(src).save(img_path)
+    np_img = np.array(Image.open(img_path).convert("RGB"), dtype=np.float32) / 255.0
+    target_img = torch.from_numpy(np_img)
+    H, W = choose_work_size(H_out, W_out, max_side=64)
+    assert (H, W) == (43, 64)
+    frames = tmp_path / "frames"
+    frames.mkdir()
+    best, fit = genetic_approx(
+        target_img, H=H, W=W, device=DEV, pop_size=16, n_splats=48, generations=12, tour_k=C.TOUR_K,
+        elite_k=4, cxpb=C.CXPB, mutpb=C.MUTPB, mut_sigma_max=C.MUT_SIGMA_MAX,
+        mut_sigma_min=C.MUT_SIGMA_MIN, schedule=C.SCHEDULE, min_scale_splats=C.MIN_SCALE_SPLATS,
+        max_scale_splats=C.MAX_SCALE_SPLATS, k_sigma=C.K_SIGMA, mask_strength=C.MASK_STRENGTH,
+        boost_only=C.BOOST_ONLY, save_video=True, frame_every=4, video_dir=str(frames), prefix="ga",
+        loss_png_path="", loss_csv_path=str(tmp_path / "out" / "ga_loss.csv"), loss_log_y=True)
+    assert best.shape == (48, 9) and 0 < fit < 1
+    assert sorted(p.name for p in frames.iterdir()) == ["ga_00.png", "ga_04.png", "ga_08.png", "ga_12.png"]
+    rows = (tmp_path / "out" / "ga_loss.csv").read_text().strip().splitlines()
+    assert rows[0] == "gen,best,mean,median" and len(rows) == 14
+    full = scale_genome_pixels_anisotropic(best.to(DEV), sH=H_out / float(H), sW=W_out / float(W))
+    final = render_splats_rgb_triton(genome_to_renderer(full).unsqueeze(0), H_out, W_out,
+                                     k_sigma=C.K_SIGMA, device=DEV, tile=C.DEFAULT_TILE_SIZE)[0]
+    img8 = (final.clamp(0, 1).detach().cpu().numpy() * 255).astype("uint8")
+    assert img8.shape == (H_out, W_out, 3)
+    Image.fromarray(img8).save(tmp_path / "ga_splats.png")
