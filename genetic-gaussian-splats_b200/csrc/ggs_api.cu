@@ -259,19 +259,23 @@ int ggs_fitness(const float *d_genomes, int layout, int B, int N, int cols, int 
 /* ---------------------------------------------------------------------------------- */
 /* host-buffer path                                                                    */
 
+constexpr int kMaxSlices = 8;
+
 struct ggs_ctx {
     int device = 0;
-    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaStream_t copy = nullptr;                // host -> device genome slices, running ahead
+    cudaStream_t stream[2] = {nullptr, nullptr};  // compute, alternating per slice
+    cudaEvent_t landed[kMaxSlices] = {};        // slice k is on the device
     cudaEvent_t done[2] = {nullptr, nullptr};
     float *d_target = nullptr;
     float *d_mask = nullptr;
     int H = 0, W = 0;
     bool has_mask = false;
-    // per-stream slice buffers (grow-only)
-    float *d_genomes[2] = {nullptr, nullptr};
-    size_t genomes_cap[2] = {0, 0};
-    void *d_ws[2] = {nullptr, nullptr};
-    size_t ws_cap[2] = {0, 0};
+    // grow-only device buffers: the whole population's genomes, one workspace per slice
+    float *d_genomes = nullptr;
+    size_t genomes_cap = 0;
+    void *d_ws[kMaxSlices] = {};
+    size_t ws_cap[kMaxSlices] = {};
     float *d_fitness = nullptr;
     size_t fitness_cap = 0;
 };
@@ -307,10 +311,13 @@ int ggs_ctx_create(int device, ggs_ctx **out)
         return GGS_EINVAL;
     }
     c->device = device;
+    GGS_CUDA(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         GGS_CUDA(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
         GGS_CUDA(cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < kMaxSlices; ++i)
+        GGS_CUDA(cudaEventCreateWithFlags(&c->landed[i], cudaEventDisableTiming));
     *out = c;
     return GGS_OK;
 }
@@ -319,13 +326,18 @@ void ggs_ctx_destroy(ggs_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->copy) cudaStreamSynchronize(c->copy);
     for (int i = 0; i < 2; ++i) {
         if (c->stream[i]) cudaStreamSynchronize(c->stream[i]);
-        if (c->d_genomes[i]) cudaFree(c->d_genomes[i]);
-        if (c->d_ws[i]) cudaFree(c->d_ws[i]);
         if (c->done[i]) cudaEventDestroy(c->done[i]);
         if (c->stream[i]) cudaStreamDestroy(c->stream[i]);
     }
+    for (int i = 0; i < kMaxSlices; ++i) {
+        if (c->landed[i]) cudaEventDestroy(c->landed[i]);
+        if (c->d_ws[i]) cudaFree(c->d_ws[i]);
+    }
+    if (c->copy) cudaStreamDestroy(c->copy);
+    if (c->d_genomes) cudaFree(c->d_genomes);
     if (c->d_target) cudaFree(c->d_target);
     if (c->d_mask) cudaFree(c->d_mask);
     if (c->d_fitness) cudaFree(c->d_fitness);
@@ -341,6 +353,7 @@ int ggs_ctx_set_target(ggs_ctx *c, const float *h_target, const float *h_mask, i
     int rc = check_shape(0, 0, 9, H, W);
     if (rc) return rc;
     GGS_CUDA(cudaSetDevice(c->device));
+    GGS_CUDA(cudaStreamSynchronize(c->copy));
     for (int i = 0; i < 2; ++i) GGS_CUDA(cudaStreamSynchronize(c->stream[i]));
     if (c->d_target) GGS_CUDA(cudaFree(c->d_target));
     if (c->d_mask) GGS_CUDA(cudaFree(c->d_mask));
@@ -380,30 +393,43 @@ int ggs_ctx_fitness_host(ggs_ctx *c, const float *h_genomes, int layout, int B, 
     }
     GGS_CUDA(cudaSetDevice(c->device));
 
-    // Slices alternate between two streams so the H2D copy of slice k+1 overlaps the kernels
-    // of slice k.  Slice = at most a quarter of the population, at least 64 candidates.
-    const int slice = std::max(64, (B + 3) / 4);
+    // The genomes go up in slices on a copy stream that runs ahead of the compute streams;
+    // slice k is evaluated as soon as it has landed.  Sizes double (B/16, B/8, B/4, rest), so
+    // only a sixteenth of the copy is exposed and every later copy hides behind the previous,
+    // smaller, evaluation; consecutive slices use alternating compute streams so the tail of
+    // one raster overlaps the head of the next.
+    int start[kMaxSlices + 1];
+    int ns = 0;
+    start[0] = 0;
+    for (int sz = std::max(32, B / 16); start[ns] < B && ns < kMaxSlices; sz *= 2) {
+        const bool last = (ns == 3) || (ns == kMaxSlices - 1) || start[ns] + sz >= B;
+        start[ns + 1] = last ? B : start[ns] + sz;
+        ++ns;
+    }
     const size_t row_bytes = (size_t)N * cols * sizeof(float);
     rc = grow(reinterpret_cast<void **>(&c->d_fitness), &c->fitness_cap, (size_t)B * sizeof(float));
     if (rc) return rc;
-    for (int i = 0; i < 2; ++i) {
-        const int sb = std::min(slice, B);
-        rc = grow(reinterpret_cast<void **>(&c->d_genomes[i]), &c->genomes_cap[i],
-                  std::max<size_t>(sb * row_bytes, 256));
-        if (rc) return rc;
-        rc = grow(&c->d_ws[i], &c->ws_cap[i], workspace_bytes(sb, N, c->H, c->W));
+    rc = grow(reinterpret_cast<void **>(&c->d_genomes), &c->genomes_cap,
+              std::max<size_t>((size_t)B * row_bytes, 256));
+    if (rc) return rc;
+    for (int k = 0; k < ns; ++k) {
+        rc = grow(&c->d_ws[k], &c->ws_cap[k], workspace_bytes(start[k + 1] - start[k], N, c->H, c->W));
         if (rc) return rc;
     }
     const float white[3] = {1.0f, 1.0f, 1.0f};
-    int k = 0;
-    for (int b0 = 0; b0 < B; b0 += slice, ++k) {
-        const int sb = std::min(slice, B - b0);
-        const int s = k & 1;
-        GGS_CUDA(cudaMemcpyAsync(c->d_genomes[s], h_genomes + (size_t)b0 * N * cols, sb * row_bytes,
-                                 cudaMemcpyHostToDevice, c->stream[s]));
-        rc = evaluate(c->d_genomes[s], layout, sb, N, cols, c->H, c->W, k_sigma, white, c->d_target,
-                      c->d_mask, mode, boost_beta, c->d_fitness + b0, nullptr, 0, c->d_ws[s],
-                      c->ws_cap[s], c->stream[s]);
+    for (int k = 0; k < ns; ++k) {
+        const size_t off = (size_t)start[k] * N * cols;
+        GGS_CUDA(cudaMemcpyAsync(c->d_genomes + off, h_genomes + off,
+                                 (size_t)(start[k + 1] - start[k]) * row_bytes,
+                                 cudaMemcpyHostToDevice, c->copy));
+        GGS_CUDA(cudaEventRecord(c->landed[k], c->copy));
+    }
+    for (int k = 0; k < ns; ++k) {
+        const int s = k & 1, sb = start[k + 1] - start[k];
+        GGS_CUDA(cudaStreamWaitEvent(c->stream[s], c->landed[k], 0));
+        rc = evaluate(c->d_genomes + (size_t)start[k] * N * cols, layout, sb, N, cols, c->H, c->W,
+                      k_sigma, white, c->d_target, c->d_mask, mode, boost_beta,
+                      c->d_fitness + start[k], nullptr, 0, c->d_ws[k], c->ws_cap[k], c->stream[s]);
         if (rc) return rc;
     }
     // Drain: stream 1's work must finish before the single D2H issued on stream 0.
