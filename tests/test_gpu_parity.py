@@ -453,3 +453,39 @@ def test_uint8_frames_match_the_reference_conversion(ggs, golden):
     frame = render_axes_angle_to_img(cuda(golden["axes"])[0], H, W, k, "cuda")
     assert frame.dtype == np.uint8 and frame.shape == (H, W, 3)
     assert np.abs(frame.astype(np.int16) - ref8[0]).max() <= 1
+
+
+def test_randomised_shapes_against_oracle(ggs):
+    """Seeded fuzz over image sizes, splat counts, k_sigma, layouts, backgrounds and modes."""
+    from ggs_b200 import synth
+    rng = np.random.default_rng(2024)
+    n_flips = 0
+    for trial in range(24):
+        H, W = int(rng.integers(1, 180)), int(rng.integers(1, 180))
+        N, B = int(rng.integers(0, 260)), int(rng.integers(1, 5))
+        k = float(rng.choice([1.0, 2.0, 3.0, 4.5]))
+        g = synth.new_population_np(B, max(N, 1), H, W, seed=100 + trial)[:, :N]
+        if N and trial % 3 == 0:                      # sprinkle degenerate genes
+            g[0, 0, 2:4] = rng.uniform(-6.0, 6.0, size=2)
+            g[0, N // 2, 8] = 0.0
+            g[-1, -1, 0:2] = rng.uniform(-0.5, 1.5, size=2)
+        t = synth.synthetic_target_np(H, W, trial)
+        m = rng.uniform(0.2, 1.3, size=(H, W)).astype(np.float32)   # also exercises clamp(w,0,1)
+        bg = tuple(float(v) for v in rng.uniform(0, 1, size=3))
+
+        chol = oracle.encode(g)
+        dec_g = to_np(ggs.decode(cuda(g), H, W, k, layout=ggs.LAYOUT_AXES_ANGLE)) if N else None
+        bad = aabb_mismatch_mask(dec_g, oracle.decode(chol, H, W, k)) if N else np.zeros((B, 0), bool)
+        n_flips += int(bad.sum())
+        if bad.any():
+            continue                                  # counted, reported below, not hidden
+        img_ref = oracle.render(chol, H, W, k, background=bg)
+        img = ggs.render(cuda(chol), H, W, k, background=bg).cpu().numpy()
+        assert np.abs(img - img_ref).max() <= IMG_TOL, (trial, H, W, N, B, k)
+        for kw in ({}, {"weight_mask": m}, {"weight_mask": m, "boost_only": True}):
+            f_ref = oracle.fitness(g, t, H, W, k, **kw)
+            kw_gpu = {a: (cuda(v) if isinstance(v, np.ndarray) else v) for a, v in kw.items()}
+            f = ggs.fitness(cuda(g), cuda(t), H, W, k, **kw_gpu).cpu().numpy()
+            np.testing.assert_allclose(f, f_ref, rtol=FIT_RTOL, err_msg=str((trial, H, W, N, B, k, list(kw))))
+    print(f"AABB flips over the fuzz set: {n_flips}")
+    assert n_flips <= 2
