@@ -26,9 +26,9 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path
 # per-file extra flags: the decode must not contract mul+add (bit-exact AABB, SURVEY finding 4)
 SOURCES = {
     "ggs_decode.cu": ["-fmad=false"],
-    # ptxas -O3 renames the packed (64-bit) pixel accumulators out of place and pays ~20
-    # MOV/IMAD.MOV per splat to move them back; -O1 keeps FFMA2/FADD2 in place (checked in SASS)
-    "ggs_raster.cu": ["-Xptxas", "-O1"],
+    # the packed (64-bit) pixel accumulators live in named PTX registers (GGS_NAMED_REGS), which
+    # keeps ptxas from renaming them out of place at any -O level; tests/test_cpu_sass.py guards it
+    "ggs_raster.cu": [],
     "ggs_breed.cu": [],
     "ggs_probe.cu": [],
     "ggs_api.cu": [],

@@ -38,13 +38,19 @@ namespace {
 #define GGS_ILP 0
 #endif
 #ifndef GGS_MIN_BLOCKS
-#define GGS_MIN_BLOCKS 7
+#define GGS_MIN_BLOCKS 8
 #endif
 #ifndef GGS_SATURATE
 #define GGS_SATURATE 1
 #endif
 #ifndef GGS_PREFETCH
 #define GGS_PREFETCH 0
+#endif
+#ifndef GGS_CP_ASYNC
+#define GGS_CP_ASYNC 1
+#endif
+#ifndef GGS_NAMED_REGS
+#define GGS_NAMED_REGS 1
 #endif
 
 constexpr int kPairs = kRowsPerThread / 2;
@@ -59,6 +65,15 @@ __device__ __forceinline__ float ex2_approx(float x)
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+
+// 16-byte asynchronous global -> shared copy (SASS LDGSTS), cached in L1: the tiles of one
+// candidate run on neighbouring CTAs and re-read the same records.
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 
@@ -144,7 +159,37 @@ __device__ __forceinline__ unsigned lane_mask(int x0, int x1, int X0)
 }
 
 // One row pair, front to back (render.py:194-196 rearranged): W = F*T, C += W*col, T -= W.
-#define GGS_BLEND_PAIR(k, F_)                 \
+#if GGS_NAMED_REGS
+// The pixel state lives in PTX registers declared once per kernel (ggs_r0..3, ggs_g0..3,
+// ggs_b0..3, ggs_t0..3) and is only ever touched by in-place PTX: ptxas sees sixteen registers
+// that are updated where they are, whatever the control flow around them looks like, and has
+// no SSA copies of the accumulators to (mis)coalesce.
+#define GGS_PX_DECLARE() asm volatile(".reg .b64 ggs_r<4>, ggs_g<4>, ggs_b<4>, ggs_t<4>;")
+#define GGS_PX_INIT(k, ta_, tb_)                                                        \
+    asm volatile("mov.b64 ggs_r" #k ", 0;\n\tmov.b64 ggs_g" #k ", 0;\n\tmov.b64 ggs_b" #k \
+                 ", 0;\n\tmov.b64 ggs_t" #k ", {%0, %1};" ::"f"(ta_), "f"(tb_))
+#define GGS_PX_BLEND(k, F_)                                                             \
+    asm volatile("{\n\t.reg .b64 w;\n\t"                                               \
+                 "mul.rn.f32x2 w, %0, ggs_t" #k ";\n\t"                                 \
+                 "fma.rn.f32x2 ggs_r" #k ", w, %1, ggs_r" #k ";\n\t"                    \
+                 "fma.rn.f32x2 ggs_g" #k ", w, %2, ggs_g" #k ";\n\t"                    \
+                 "fma.rn.f32x2 ggs_b" #k ", w, %3, ggs_b" #k ";\n\t"                    \
+                 "sub.rn.f32x2 ggs_t" #k ", ggs_t" #k ", w;\n\t}" ::"l"(F_),            \
+                 "l"(R2), "l"(G2), "l"(B2));
+#define GGS_PX_READ_T(k, a_, b_) asm volatile("mov.b64 {%0, %1}, ggs_t" #k ";" : "=f"(a_), "=f"(b_))
+#define GGS_PX_READ(k, r_, g_, b_, t_)                                                  \
+    asm volatile("mov.b64 {%0, %1}, ggs_r" #k ";\n\tmov.b64 {%2, %3}, ggs_g" #k          \
+                 ";\n\tmov.b64 {%4, %5}, ggs_b" #k ";\n\tmov.b64 {%6, %7}, ggs_t" #k ";" \
+                 : "=f"(r_[0]), "=f"(r_[1]), "=f"(g_[0]), "=f"(g_[1]), "=f"(b_[0]),     \
+                   "=f"(b_[1]), "=f"(t_[0]), "=f"(t_[1]))
+#else
+#define GGS_PX_DECLARE()
+#define GGS_PX_INIT(k, ta_, tb_)                    \
+    {                                               \
+        px.r[k] = px.g[k] = px.b[k] = bcast2(0.0f); \
+        px.t[k] = pack2(ta_, tb_);                  \
+    }
+#define GGS_PX_BLEND(k, F_)                   \
     {                                         \
         const f2_t Wk = mul2(F_, px.t[k]);    \
         fma2_acc(px.r[k], Wk, R2);            \
@@ -152,6 +197,15 @@ __device__ __forceinline__ unsigned lane_mask(int x0, int x1, int X0)
         fma2_acc(px.b[k], Wk, B2);            \
         sub2_acc(px.t[k], Wk);                \
     }
+#define GGS_PX_READ_T(k, a_, b_) unpack2(px.t[k], a_, b_)
+#define GGS_PX_READ(k, r_, g_, b_, t_)    \
+    {                                     \
+        unpack2(px.r[k], r_[0], r_[1]);   \
+        unpack2(px.g[k], g_[0], g_[1]);   \
+        unpack2(px.b[k], b_[0], b_[1]);   \
+        unpack2(px.t[k], t_[0], t_[1]);   \
+    }
+#endif
 
 // Blend the staged list (reverse genome order) into this thread's pixels.  The exponent of the
 // falloff on row i of the thread's column is e(i) = (Cq*qy + t1)*qy + t0 with qy = dy + i
@@ -188,10 +242,10 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
 #if GGS_SATURATE
         if ((s & (kSatEvery - 1)) == kSatEvery - 1) {
             float t0a, t1a, t2a, t3a, t4a, t5a, t6a, t7a;
-            unpack2(px.t[0], t0a, t1a);
-            unpack2(px.t[1], t2a, t3a);
-            unpack2(px.t[2], t4a, t5a);
-            unpack2(px.t[3], t6a, t7a);
+            GGS_PX_READ_T(0, t0a, t1a);
+            GGS_PX_READ_T(1, t2a, t3a);
+            GGS_PX_READ_T(2, t4a, t5a);
+            GGS_PX_READ_T(3, t6a, t7a);
             const float tmax = fmaxf(fmaxf(fmaxf(t0a, t1a), fmaxf(t2a, t3a)),
                                      fmaxf(fmaxf(t4a, t5a), fmaxf(t6a, t7a)));
             if (__all_sync(0xffffffffu, tmax < kOpaque)) return false;
@@ -221,52 +275,34 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
             f2_t G = pack2(ex2_approx(d0), ex2_approx(d1));
             const f2_t H2 = bcast2(q2.w);
             if (kStats) work[0] += kPairs;
-#if GGS_ILP
-            // recurrence first, then four independent blends: more packed ops in flight
-            f2_t Fk[kPairs];
-            Fk[0] = F;
-#pragma unroll
-            for (int k = 1; k < kPairs; ++k) {
-                Fk[k] = mul2(Fk[k - 1], G);
-                if (k + 1 < kPairs) mul2_acc(G, H2);
-            }
-            f2_t Wk[kPairs];
-#pragma unroll
-            for (int k = 0; k < kPairs; ++k) Wk[k] = mul2(Fk[k], px.t[k]);
-#pragma unroll
-            for (int k = 0; k < kPairs; ++k) fma2_acc(px.r[k], Wk[k], R2);
-#pragma unroll
-            for (int k = 0; k < kPairs; ++k) fma2_acc(px.g[k], Wk[k], G2);
-#pragma unroll
-            for (int k = 0; k < kPairs; ++k) fma2_acc(px.b[k], Wk[k], B2);
-#pragma unroll
-            for (int k = 0; k < kPairs; ++k) sub2_acc(px.t[k], Wk[k]);
-#else
-#pragma unroll
-            for (int k = 0; k < kPairs; ++k) {
-                GGS_BLEND_PAIR(k, F)
-                if (k + 1 < kPairs) {
-                    mul2_acc(F, G);
-                    mul2_acc(G, H2);
-                }
-            }
-#endif
+            GGS_PX_BLEND(0, F)
+            mul2_acc(F, G);
+            mul2_acc(G, H2);
+            GGS_PX_BLEND(1, F)
+            mul2_acc(F, G);
+            mul2_acc(G, H2);
+            GGS_PX_BLEND(2, F)
+            mul2_acc(F, G);
+            GGS_PX_BLEND(3, F)
         } else {
             const int lo = (int)(c & 7u), hi = (int)(c >> 4);
-#pragma unroll
-            for (int k = 0; k < kPairs; ++k) {
-                if (2 * k + 1 >= lo && 2 * k <= hi) {
-                    const f2_t QYk = add2(QY, bcast2((float)(2 * k)));
-                    const f2_t E = fma2(fma2(CQ2, QYk, T12), QYk, T02);
-                    float e0, e1;
-                    unpack2(E, e0, e1);
-                    const float f0 = (2 * k >= lo) ? ex2_approx(e0) : 0.0f;
-                    const float f1 = (2 * k + 1 <= hi) ? ex2_approx(e1) : 0.0f;
-                    const f2_t F = pack2(f0, f1);
-                    if (kStats) work[1] += 1;
-                    GGS_BLEND_PAIR(k, F)
-                }
-            }
+#define GGS_EXACT_PAIR(k)                                                          \
+    if (2 * k + 1 >= lo && 2 * k <= hi) {                                          \
+        const f2_t QYk = add2(QY, bcast2((float)(2 * k)));                         \
+        const f2_t E = fma2(fma2(CQ2, QYk, T12), QYk, T02);                        \
+        float e0, e1;                                                              \
+        unpack2(E, e0, e1);                                                        \
+        const float f0 = (2 * k >= lo) ? ex2_approx(e0) : 0.0f;                    \
+        const float f1 = (2 * k + 1 <= hi) ? ex2_approx(e1) : 0.0f;                \
+        const f2_t F = pack2(f0, f1);                                              \
+        if (kStats) work[1] += 1;                                                  \
+        GGS_PX_BLEND(k, F)                                                         \
+    }
+            GGS_EXACT_PAIR(0)
+            GGS_EXACT_PAIR(1)
+            GGS_EXACT_PAIR(2)
+            GGS_EXACT_PAIR(3)
+#undef GGS_EXACT_PAIR
         }
     }
     return true;
@@ -301,12 +337,15 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
     // Transmittance starts at 1 inside the image and at 0 outside it: pixels beyond the image
     // edge then take no colour and never keep a band from saturating.
     Pixels px;
-#pragma unroll
-    for (int k = 0; k < kPairs; ++k) {
-        px.r[k] = px.g[k] = px.b[k] = bcast2(0.0f);
-        px.t[k] = pack2((X < W && Yb + 2 * k < H) ? 1.0f : 0.0f,
-                        (X < W && Yb + 2 * k + 1 < H) ? 1.0f : 0.0f);
-    }
+    GGS_PX_DECLARE();
+#define GGS_T_INIT(k)                                              \
+    GGS_PX_INIT(k, (X < W && Yb + 2 * k < H) ? 1.0f : 0.0f,        \
+                (X < W && Yb + 2 * k + 1 < H) ? 1.0f : 0.0f)
+    GGS_T_INIT(0);
+    GGS_T_INIT(1);
+    GGS_T_INIT(2);
+    GGS_T_INIT(3);
+#undef GGS_T_INIT
     bool live = true;  // warp-uniform: this band still has a non-opaque pixel
 
     const float4 *recb = rec + (int64_t)b * N * 3;
@@ -355,13 +394,21 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
                 const bool steep = q2.w < 0.0f;
                 q2.y = __uint_as_float(lane_mask(bx0[j], bx1[j], X0));
                 q2.z = __uint_as_float(row_code(by0[j], by1[j], Y0, steep));
+#if GGS_CP_ASYNC
+                cp_async16(&s_list[pos * 3 + 0], src + 0);  // LDGSTS: no register staging
+                cp_async16(&s_list[pos * 3 + 1], src + 1);
+#else
                 s_list[pos * 3 + 0] = __ldg(src + 0);
                 s_list[pos * 3 + 1] = __ldg(src + 1);
+#endif
                 s_list[pos * 3 + 2] = q2;
             }
             run += tot;
         }
         cnt = run;
+#if GGS_CP_ASYNC
+        cp_async_wait_all();
+#endif
         __syncthreads();
         if (cnt > kListCap - kScanChunk || top <= kScanChunk) {
             if (live) live = composite_list<kStats>(s_list, cnt, lanebit, band_sel, Xf, Ybf, px, work);
@@ -375,14 +422,15 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
     // clamp (render.py:252), optional image store, squared error (fitness.py:16-31).
     float num = 0.0f, den = 0.0f;
     const bool want_fit = (target != nullptr);
+    float prr[kPairs][2], pgg[kPairs][2], pbb[kPairs][2], ptt[kPairs][2];
+    GGS_PX_READ(0, prr[0], pgg[0], pbb[0], ptt[0]);
+    GGS_PX_READ(1, prr[1], pgg[1], pbb[1], ptt[1]);
+    GGS_PX_READ(2, prr[2], pgg[2], pbb[2], ptt[2]);
+    GGS_PX_READ(3, prr[3], pgg[3], pbb[3], ptt[3]);
 #pragma unroll
     for (int i = 0; i < kRowsPerThread; ++i) {
         const int Y = Yb + i;
-        float pr[2], pg[2], pb[2], pt[2];
-        unpack2(px.r[i >> 1], pr[0], pr[1]);
-        unpack2(px.g[i >> 1], pg[0], pg[1]);
-        unpack2(px.b[i >> 1], pb[0], pb[1]);
-        unpack2(px.t[i >> 1], pt[0], pt[1]);
+        const float *pr = prr[i >> 1], *pg = pgg[i >> 1], *pb = pbb[i >> 1], *pt = ptt[i >> 1];
         if (X < W && Y < H) {
             const float tr = pt[i & 1];
             const float cr = clamp01(fmaf(tr, bg_r, pr[i & 1]));

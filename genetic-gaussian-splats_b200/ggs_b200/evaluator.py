@@ -25,6 +25,7 @@ DECODE_FLOAT_KEYS = ("cx", "cy", "sxx", "sxy", "syy", "rc", "gc", "bc", "a")
 DECODE_INT_KEYS = ("x0", "x1", "y0", "y1")
 
 _workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+_retired: list = []
 
 
 def _cuda_device(device) -> torch.device:
@@ -48,6 +49,10 @@ def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
     key = (dev.index, _stream_ptr(dev))
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            # a captured CUDA graph may still point at the old buffer: retire it, never free it
+            _retired.append(ws)
+            nbytes = max(nbytes, ws.numel() * 3 // 2)   # geometric growth bounds what is retired
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
         _workspaces[key] = ws
     return ws

@@ -1,0 +1,60 @@
+"""Code-generation guard for the raster kernel (CPU only: cuobjdump reads the built object).
+
+The recurrence path must stay a copy-free run of packed FP32 instructions.  ptxas sometimes
+renames the 64-bit accumulators out of place and then pays ~20 MOV / IMAD.MOV per splat to
+move them back (seen with -O3 and after innocuous source edits: 9-11 % slower on the B200,
+DESIGN.md section 4.2), so this is checked where it is cheap to check."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OBJ = os.path.join(ROOT, "genetic-gaussian-splats_b200", "build", "ggs_raster.o")
+
+
+def production_kernel_sass():
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    if not os.path.exists(OBJ):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location(
+            "ggs_build", os.path.join(ROOT, "genetic-gaussian-splats_b200", "build.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.build()
+    text = subprocess.run(["cuobjdump", "-sass", OBJ], capture_output=True, text=True, check=True).stdout
+    funcs = re.split(r"\n\s*Function : ", text)
+    prod = [f for f in funcs if "raster_kernelILb0E" in f.split("\n", 1)[0]]
+    assert len(prod) == 1, "raster_kernel<false> not found in the object"
+    ops = []
+    for line in prod[0].splitlines():
+        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?)\s*;", line)
+        if m:
+            ops.append(m.group(1))
+    return ops
+
+
+def test_packed_fp32_and_mufu_are_in_the_kernel():
+    ops = production_kernel_sass()
+    names = [o.split()[1] if o.startswith("@") else o.split()[0] for o in ops]
+    assert sum(n.startswith("FFMA2") for n in names) >= 20
+    assert sum(n.startswith("FMUL2") for n in names) >= 8
+    assert sum(n.startswith("FADD2") for n in names) >= 4
+    assert sum(n.startswith("MUFU.EX2") for n in names) >= 8
+    assert not any(n.startswith(("STL", "LDL")) for n in names), "register spills in the raster kernel"
+
+
+def test_recurrence_path_has_no_register_copies():
+    ops = production_kernel_sass()
+    first = next(i for i, o in enumerate(ops) if "MUFU.EX2" in o)
+    # the recurrence block: from its first MUFU.EX2 to the BRA that closes it
+    end = next(i for i in range(first, len(ops)) if re.match(r"(@!?U?P\d+\s+)?BRA\b", ops[i]))
+    block = ops[first:end]
+    packed = [o for o in block if re.search(r"\b(FFMA2|FMUL2|FADD2)\b", o)]
+    copies = [o for o in block if re.match(r"(IMAD\.MOV|MOV)\b", o)]
+    assert len(packed) >= 24, block
+    assert len(copies) <= 2, f"{len(copies)} register copies in the recurrence path:\n" + "\n".join(block)
+    assert len(block) <= len(packed) + 12
