@@ -52,10 +52,17 @@ namespace {
 #ifndef GGS_NAMED_REGS
 #define GGS_NAMED_REGS 1
 #endif
+#ifndef GGS_PIN_CONSTS
+#define GGS_PIN_CONSTS 2
+#endif
+#ifndef GGS_UNROLL
+#define GGS_UNROLL 1
+#endif
 
 constexpr int kPairs = kRowsPerThread / 2;
 constexpr int kScanPerThread = 2;
 constexpr int kScanChunk = kThreads * kScanPerThread;  // records examined per round
+constexpr int kListUnroll = GGS_UNROLL;
 constexpr int kSatEvery = 8;                           // list entries between saturation votes
 constexpr float kOpaque = 2.384185791015625e-07f;      // 2^-22: transmittance counted as zero
 
@@ -232,6 +239,7 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
 #if GGS_PREFETCH
     float4 q2_next = list[2];  // entry 0; the loop keeps the next entry's q2 in flight
 #endif
+#pragma unroll kListUnroll
     for (int s = 0; s < cnt; ++s) {
 #if GGS_PREFETCH
         const float4 q2 = q2_next;
@@ -330,9 +338,21 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
     const int X0 = tx * kTileW, Y0 = ty * kTileH;
     const int X1 = X0 + kTileW - 1, Y1 = Y0 + kTileH - 1;
     const int X = X0 + lane, Yb = Y0 + warp * kRowsPerThread;
+#if GGS_PIN_CONSTS >= 2
+    const float Xf = __shfl_sync(0xffffffffu, (float)X, lane);   // pinned like lanebit below
+    const float Ybf = __shfl_sync(0xffffffffu, (float)Yb, lane);
+#else
     const float Xf = (float)X, Ybf = (float)Yb;
+#endif
+#if GGS_PIN_CONSTS
+    // Routed through a shuffle so ptxas cannot rematerialise them from %tid.x inside the
+    // composite loop (it otherwise re-reads the special register once per list entry).
+    const unsigned lanebit = __shfl_sync(0xffffffffu, 1u << lane, lane);
+    const unsigned band_sel = __shfl_sync(0xffffffffu, 0x4440u + (unsigned)warp, lane);
+#else
     const unsigned lanebit = 1u << lane;
     const unsigned band_sel = 0x4440u + (unsigned)warp;  // PRMT: byte `warp`, zero-extended
+#endif
 
     // Transmittance starts at 1 inside the image and at 0 outside it: pixels beyond the image
     // edge then take no colour and never keep a band from saturating.

@@ -44,7 +44,12 @@ def test_packed_fp32_and_mufu_are_in_the_kernel():
     assert sum(n.startswith("FMUL2") for n in names) >= 8
     assert sum(n.startswith("FADD2") for n in names) >= 4
     assert sum(n.startswith("MUFU.EX2") for n in names) >= 8
-    assert not any(n.startswith(("STL", "LDL")) for n in names), "register spills in the raster kernel"
+    # a few spilled bytes are tolerated in the kernel prologue / epilogue, never in the
+    # composite loop (from its first list load to the last exact-path MUFU.EX2)
+    mufu = [i for i, n in enumerate(names) if n.startswith("MUFU.EX2")]
+    hot = names[max(0, mufu[0] - 45): mufu[-1] + 20]
+    assert not any(n.startswith(("STL", "LDL")) for n in hot), "local-memory traffic in the composite loop"
+    assert not any(n.startswith(("S2R", "I2FP")) for n in hot), "thread constants rematerialised in the loop"
 
 
 def test_recurrence_path_has_no_register_copies():
