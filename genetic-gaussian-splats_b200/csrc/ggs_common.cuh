@@ -13,8 +13,16 @@ namespace ggs {
 // is warp-uniform (no per-pixel predicate) and the AABB column test is one select per
 // (thread, splat) folded into the exponent.
 constexpr int kTileW = 32;
-constexpr int kRowsPerThread = 8;
-constexpr int kWarps = 4;
+#ifndef GGS_ROWS
+#define GGS_ROWS 8    // pixel rows per thread: 8 or 16 (row codes hold 4-bit row indices)
+#endif
+#ifndef GGS_WARPS
+#define GGS_WARPS 4   // warps (bands) per CTA, <= 4 (one row-code byte per band)
+#endif
+static_assert(GGS_ROWS == 8 || GGS_ROWS == 16, "rows per thread must be 8 or 16");
+static_assert(GGS_WARPS >= 1 && GGS_WARPS <= 4, "1..4 warps per CTA");
+constexpr int kRowsPerThread = GGS_ROWS;
+constexpr int kWarps = GGS_WARPS;
 constexpr int kTileH = kWarps * kRowsPerThread;
 constexpr int kThreads = kWarps * 32;
 constexpr int kListCap = 512;  // staged splat records per flush (48 B each)

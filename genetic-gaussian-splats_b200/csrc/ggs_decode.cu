@@ -195,11 +195,12 @@ decode_kernel(const float *__restrict__ genomes, int cols, int64_t rows, int H, 
         r.xpack = (d.x0 & 0xffff) | (d.x1 << 16);
         r.ypack = (d.y0 & 0xffff) | (d.y1 << 16);
         // Column recurrence of the raster (f(i+2) = f(i)*g(i), g(i+2) = g(i)*h): h = 2^(8*Cq).
-        // It is used only while the exponent moves by < 64 across a thread's 8-row strip
+        // It is used only while the exponent moves by < 64 across a thread's strip of rows
         // anywhere a lane of the tile can sit (|qy| <= hy+1, |qx| <= hx+32); otherwise the
         // splat is marked steep (h = -1) and takes the exact per-pixel path.
-        const float swing = fabsf(r.Cq) * (14.0f * (d.hy + 1.0f) + 49.0f) +
-                            7.0f * fabsf(r.Bq) * (d.hx + 32.0f);
+        constexpr float kSpan = (float)(kRowsPerThread - 1);  // rows crossed by one strip
+        const float swing = fabsf(r.Cq) * (2.0f * kSpan * (d.hy + 1.0f) + kSpan * kSpan) +
+                            kSpan * fabsf(r.Bq) * (d.hx + (float)kTileW);
         r.h = (swing < 64.0f) ? exp2f(8.0f * r.Cq) : -1.0f;  // NaN swing compares false -> steep
         const float4 *rv = reinterpret_cast<const float4 *>(&r);
         rec[row * 3 + 0] = rv[0];

@@ -6,11 +6,12 @@
 //   canvas fill / final clamp     modules/render.py:236-237, :252
 //   squared error + reductions    modules/fitness.py:16-31
 //
-// One CTA = one (candidate, 32x32 tile).  The CTA streams the candidate's packed AABBs, 256 per
-// round; a ballot/popcount prefix compacts the splats that touch the tile *in order* into a
-// shared-memory list of 48-byte records (no global sort, no host sync), and whenever the list
-// fills (or the genome ends) the four warps composite it.  Warp w owns the 32x8 band of rows
-// [8w, 8w+8): lane = pixel column, 8 vertically adjacent pixels per thread.  With that mapping
+// One CTA = one (candidate, tile of 32 x kTileH pixels).  The CTA streams the candidate's packed
+// AABBs, 256 per round; a ballot/popcount prefix compacts the splats that touch the tile *in
+// order* into a shared-memory list of 48-byte records (no global sort, no host sync; the q0/q1
+// parts are gathered with cp.async), and whenever the list fills (or the genome ends) the warps
+// composite it.  Warp w owns the band of rows [R*w, R*w + R), R = kRowsPerThread: lane = pixel
+// column, R vertically adjacent pixels per thread.  With that mapping
 //   * the AABB row test is warp-uniform: the thread that stages a record precomputes, per band,
 //     which rows it covers (one byte per warp), so a warp classifies a splat with one PRMT;
 //   * the AABB column test is a per-tile lane mask precomputed the same way: one LOP3 + one
@@ -29,42 +30,28 @@
 // Colours stay in registers from the first splat to the fitness reduction; images are written
 // only when asked for.  Per-tile partial sums are combined in a fixed order by the last CTA of
 // each candidate, so fitness is bit-reproducible.
+//
+// Code generation notes (all measured):
+//   * the pixel state lives in *named PTX registers* that only in-place PTX touches; as C++
+//     values ptxas renamed the 64-bit accumulators out of place in most builds and paid ~20
+//     MOVs per splat (tests/test_cpu_sass.py guards this);
+//   * per-thread constants used in the loop are routed through a shuffle so ptxas cannot
+//     rematerialise them from %tid.x once per list entry.
 #include "ggs_common.cuh"
 
 namespace ggs {
 namespace {
 
-#ifndef GGS_ILP
-#define GGS_ILP 0
-#endif
 #ifndef GGS_MIN_BLOCKS
-#define GGS_MIN_BLOCKS 8
-#endif
-#ifndef GGS_SATURATE
-#define GGS_SATURATE 1
-#endif
-#ifndef GGS_PREFETCH
-#define GGS_PREFETCH 0
-#endif
-#ifndef GGS_CP_ASYNC
-#define GGS_CP_ASYNC 1
-#endif
-#ifndef GGS_NAMED_REGS
-#define GGS_NAMED_REGS 1
-#endif
-#ifndef GGS_PIN_CONSTS
-#define GGS_PIN_CONSTS 2
-#endif
-#ifndef GGS_UNROLL
-#define GGS_UNROLL 1
+#define GGS_MIN_BLOCKS (GGS_ROWS == 8 ? (GGS_WARPS == 4 ? 8 : 16) : (GGS_WARPS == 4 ? 4 : 9))
 #endif
 
 constexpr int kPairs = kRowsPerThread / 2;
-constexpr int kScanPerThread = 2;
-constexpr int kScanChunk = kThreads * kScanPerThread;  // records examined per round
-constexpr int kListUnroll = GGS_UNROLL;
-constexpr int kSatEvery = 8;                           // list entries between saturation votes
-constexpr float kOpaque = 2.384185791015625e-07f;      // 2^-22: transmittance counted as zero
+constexpr int kScanPerThread = 256 / kThreads;          // 256 records examined per round
+constexpr int kScanChunk = kThreads * kScanPerThread;
+constexpr int kSatEvery = 8;                             // list entries between saturation votes
+constexpr float kOpaque = 2.384185791015625e-07f;        // 2^-22: transmittance counted as zero
+static_assert(kScanPerThread >= 1, "at most 256 threads per CTA");
 
 __device__ __forceinline__ float ex2_approx(float x)
 {
@@ -104,56 +91,63 @@ __device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c)
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
 }
-__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b)
-{
-    f2_t d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
 __device__ __forceinline__ f2_t add2(f2_t a, f2_t b)
 {
     f2_t d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-// In-place forms: the "+l" constraint pins accumulator and result to the same register pair,
-// which keeps ptxas from shuffling the pixel state through temporaries.
-__device__ __forceinline__ void fma2_acc(f2_t &c, f2_t a, f2_t b)  // c += a*b
-{
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
-}
-__device__ __forceinline__ void sub2_acc(f2_t &c, f2_t a)  // c -= a
-{
-    asm("sub.rn.f32x2 %0, %0, %1;" : "+l"(c) : "l"(a));
-}
 __device__ __forceinline__ void mul2_acc(f2_t &c, f2_t a)  // c *= a
 {
     asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(c) : "l"(a));
 }
 
-// Pixel state of one thread: 8 vertically adjacent pixels as 4 packed row pairs (2k, 2k+1):
-// accumulated colour (premultiplied, front to back) and transmittance.
-struct Pixels {
-    f2_t r[kPairs], g[kPairs], b[kPairs], t[kPairs];
-};
+// ---- pixel state: named PTX registers ggs_{r,g,b,t}<pair> -------------------------------------
+// Pair k of a thread holds rows (2k, 2k+1) of its column: accumulated colour (premultiplied,
+// front to back) and transmittance.  GGS_PAIRS(M) expands M(0) ... M(kPairs-1).
+#if GGS_ROWS == 8
+#define GGS_PX_DECLARE() asm volatile(".reg .b64 ggs_r<4>, ggs_g<4>, ggs_b<4>, ggs_t<4>;")
+#define GGS_PAIRS(M) M(0) M(1) M(2) M(3)
+#else
+#define GGS_PX_DECLARE() asm volatile(".reg .b64 ggs_r<8>, ggs_g<8>, ggs_b<8>, ggs_t<8>;")
+#define GGS_PAIRS(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
+#endif
+#define GGS_PX_INIT(k, ta_, tb_)                                                          \
+    asm volatile("mov.b64 ggs_r" #k ", 0;\n\tmov.b64 ggs_g" #k ", 0;\n\tmov.b64 ggs_b" #k   \
+                 ", 0;\n\tmov.b64 ggs_t" #k ", {%0, %1};" ::"f"(ta_), "f"(tb_));
+// One row pair, front to back (render.py:194-196 rearranged): W = F*T, C += W*col, T -= W.
+#define GGS_PX_BLEND(k, F_)                                                               \
+    asm volatile("{\n\t.reg .b64 w;\n\t"                                                 \
+                 "mul.rn.f32x2 w, %0, ggs_t" #k ";\n\t"                                   \
+                 "fma.rn.f32x2 ggs_r" #k ", w, %1, ggs_r" #k ";\n\t"                      \
+                 "fma.rn.f32x2 ggs_g" #k ", w, %2, ggs_g" #k ";\n\t"                      \
+                 "fma.rn.f32x2 ggs_b" #k ", w, %3, ggs_b" #k ";\n\t"                      \
+                 "sub.rn.f32x2 ggs_t" #k ", ggs_t" #k ", w;\n\t}" ::"l"(F_),              \
+                 "l"(R2), "l"(G2), "l"(B2));
+#define GGS_PX_READ_T(k, a_, b_) asm volatile("mov.b64 {%0, %1}, ggs_t" #k ";" : "=f"(a_), "=f"(b_));
+#define GGS_PX_READ(k, r_, g_, b_, t_)                                                    \
+    asm volatile("mov.b64 {%0, %1}, ggs_r" #k ";\n\tmov.b64 {%2, %3}, ggs_g" #k            \
+                 ";\n\tmov.b64 {%4, %5}, ggs_b" #k ";\n\tmov.b64 {%6, %7}, ggs_t" #k ";"   \
+                 : "=f"(r_[0]), "=f"(r_[1]), "=f"(g_[0]), "=f"(g_[1]), "=f"(b_[0]),       \
+                   "=f"(b_[1]), "=f"(t_[0]), "=f"(t_[1]));
 
 // Staged record (shared memory, 3 x float4), specialised for the tile by the staging thread:
 //   q0 = cx, cy, A, Bq      q1 = Cq, la, r, g      q2 = b, lane mask, row code, h
 // lane mask: bit l set iff column X0+l lies in [x0, x1].
 // row code : byte w describes band w: 0x0f = not touched, else lo | hi << 4 (rows lo..hi of the
-//            band are inside [y0, y1]) with bit 3 set for a steep splat; 0x70 = all 8 rows of a
-//            gentle splat, the only value that takes the recurrence path.
+//            band are inside [y0, y1]); (R-1) << 4 = all rows, the only value that may take the
+//            recurrence path (and only for a gentle splat, h >= 0).
 constexpr unsigned kBandMiss = 0x0fu;
-constexpr unsigned kBandFull = 0x70u;
+constexpr unsigned kBandFull = (unsigned)(kRowsPerThread - 1) << 4;
 
-__device__ __forceinline__ unsigned row_code(int y0, int y1, int Y0, bool steep)
+__device__ __forceinline__ unsigned row_code(int y0, int y1, int Y0)
 {
     unsigned code = 0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
         const int yb = Y0 + w * kRowsPerThread;
         const int lo = max(y0 - yb, 0), hi = min(y1 - yb, kRowsPerThread - 1);
-        const unsigned c = (lo > hi) ? kBandMiss : (unsigned)(lo | (hi << 4) | (steep ? 8 : 0));
+        const unsigned c = (lo > hi) ? kBandMiss : (unsigned)(lo | (hi << 4));
         code |= c << (8 * w);
     }
     return code;
@@ -165,68 +159,19 @@ __device__ __forceinline__ unsigned lane_mask(int x0, int x1, int X0)
     return (0xffffffffu >> (31 - l1)) & (0xffffffffu << l0);
 }
 
-// One row pair, front to back (render.py:194-196 rearranged): W = F*T, C += W*col, T -= W.
-#if GGS_NAMED_REGS
-// The pixel state lives in PTX registers declared once per kernel (ggs_r0..3, ggs_g0..3,
-// ggs_b0..3, ggs_t0..3) and is only ever touched by in-place PTX: ptxas sees sixteen registers
-// that are updated where they are, whatever the control flow around them looks like, and has
-// no SSA copies of the accumulators to (mis)coalesce.
-#define GGS_PX_DECLARE() asm volatile(".reg .b64 ggs_r<4>, ggs_g<4>, ggs_b<4>, ggs_t<4>;")
-#define GGS_PX_INIT(k, ta_, tb_)                                                        \
-    asm volatile("mov.b64 ggs_r" #k ", 0;\n\tmov.b64 ggs_g" #k ", 0;\n\tmov.b64 ggs_b" #k \
-                 ", 0;\n\tmov.b64 ggs_t" #k ", {%0, %1};" ::"f"(ta_), "f"(tb_))
-#define GGS_PX_BLEND(k, F_)                                                             \
-    asm volatile("{\n\t.reg .b64 w;\n\t"                                               \
-                 "mul.rn.f32x2 w, %0, ggs_t" #k ";\n\t"                                 \
-                 "fma.rn.f32x2 ggs_r" #k ", w, %1, ggs_r" #k ";\n\t"                    \
-                 "fma.rn.f32x2 ggs_g" #k ", w, %2, ggs_g" #k ";\n\t"                    \
-                 "fma.rn.f32x2 ggs_b" #k ", w, %3, ggs_b" #k ";\n\t"                    \
-                 "sub.rn.f32x2 ggs_t" #k ", ggs_t" #k ", w;\n\t}" ::"l"(F_),            \
-                 "l"(R2), "l"(G2), "l"(B2));
-#define GGS_PX_READ_T(k, a_, b_) asm volatile("mov.b64 {%0, %1}, ggs_t" #k ";" : "=f"(a_), "=f"(b_))
-#define GGS_PX_READ(k, r_, g_, b_, t_)                                                  \
-    asm volatile("mov.b64 {%0, %1}, ggs_r" #k ";\n\tmov.b64 {%2, %3}, ggs_g" #k          \
-                 ";\n\tmov.b64 {%4, %5}, ggs_b" #k ";\n\tmov.b64 {%6, %7}, ggs_t" #k ";" \
-                 : "=f"(r_[0]), "=f"(r_[1]), "=f"(g_[0]), "=f"(g_[1]), "=f"(b_[0]),     \
-                   "=f"(b_[1]), "=f"(t_[0]), "=f"(t_[1]))
-#else
-#define GGS_PX_DECLARE()
-#define GGS_PX_INIT(k, ta_, tb_)                    \
-    {                                               \
-        px.r[k] = px.g[k] = px.b[k] = bcast2(0.0f); \
-        px.t[k] = pack2(ta_, tb_);                  \
-    }
-#define GGS_PX_BLEND(k, F_)                   \
-    {                                         \
-        const f2_t Wk = mul2(F_, px.t[k]);    \
-        fma2_acc(px.r[k], Wk, R2);            \
-        fma2_acc(px.g[k], Wk, G2);            \
-        fma2_acc(px.b[k], Wk, B2);            \
-        sub2_acc(px.t[k], Wk);                \
-    }
-#define GGS_PX_READ_T(k, a_, b_) unpack2(px.t[k], a_, b_)
-#define GGS_PX_READ(k, r_, g_, b_, t_)    \
-    {                                     \
-        unpack2(px.r[k], r_[0], r_[1]);   \
-        unpack2(px.g[k], g_[0], g_[1]);   \
-        unpack2(px.b[k], b_[0], b_[1]);   \
-        unpack2(px.t[k], t_[0], t_[1]);   \
-    }
-#endif
-
 // Blend the staged list (reverse genome order) into this thread's pixels.  The exponent of the
 // falloff on row i of the thread's column is e(i) = (Cq*qy + t1)*qy + t0 with qy = dy + i
 // (render.py:189-192 with the constants folded at decode time), f = 2^e.
 //
-// Recurrence path (splat covers all 8 rows of the band, exponent varies gently): along the
+// Recurrence path (splat covers all rows of the band, exponent varies gently): along the
 // column f is the exponential of a quadratic, so with stride-2 steps
 //     f(i+2) = f(i) * g(i),   g(i+2) = g(i) * h,   h = 2^(8*Cq)
-// the 8 falloffs come from 4 MUFU.EX2 (f0, f1, g0, g1) and packed multiplies: 7 packed FMA-pipe
-// operations per row pair in all.
+// the falloffs of a whole column come from 4 MUFU.EX2 (f0, f1, g0, g1) and packed multiplies:
+// 7 packed FMA-pipe operations per row pair in all.
 // Exact path (partial band, or a "steep" splat whose exponent changes too fast for the
 // recurrence to stay accurate): Horner + one MUFU.EX2 per pixel; rows outside [y0, y1] get
 // f = 0 (an exact no-op) through warp-uniform selects, whole pairs are skipped by uniform
-// branches.  Both paths keep the pixel state in packed register pairs.
+// branches.
 //
 // Saturation: once every pixel of the band has transmittance below kOpaque, nothing further
 // back can change a pixel by more than kOpaque (colours are in [0,1]), so the warp stops
@@ -234,31 +179,22 @@ __device__ __forceinline__ unsigned lane_mask(int x0, int x1, int X0)
 template <bool kStats>
 __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, int cnt,
                                                unsigned lanebit, unsigned band_sel, float Xf,
-                                               float Ybf, Pixels &px, unsigned (&work)[2])
+                                               float Ybf, unsigned (&work)[2])
 {
-#if GGS_PREFETCH
-    float4 q2_next = list[2];  // entry 0; the loop keeps the next entry's q2 in flight
-#endif
-#pragma unroll kListUnroll
     for (int s = 0; s < cnt; ++s) {
-#if GGS_PREFETCH
-        const float4 q2 = q2_next;
-        q2_next = list[3 * min(s + 1, cnt - 1) + 2];
-#else
         const float4 q2 = list[3 * s + 2];
-#endif
-#if GGS_SATURATE
         if ((s & (kSatEvery - 1)) == kSatEvery - 1) {
-            float t0a, t1a, t2a, t3a, t4a, t5a, t6a, t7a;
-            GGS_PX_READ_T(0, t0a, t1a);
-            GGS_PX_READ_T(1, t2a, t3a);
-            GGS_PX_READ_T(2, t4a, t5a);
-            GGS_PX_READ_T(3, t6a, t7a);
-            const float tmax = fmaxf(fmaxf(fmaxf(t0a, t1a), fmaxf(t2a, t3a)),
-                                     fmaxf(fmaxf(t4a, t5a), fmaxf(t6a, t7a)));
+            float tmax = 0.0f;
+#define GGS_TMAX(k)                        \
+    {                                      \
+        float ta, tb;                      \
+        GGS_PX_READ_T(k, ta, tb)           \
+        tmax = fmaxf(tmax, fmaxf(ta, tb)); \
+    }
+            GGS_PAIRS(GGS_TMAX)
+#undef GGS_TMAX
             if (__all_sync(0xffffffffu, tmax < kOpaque)) return false;
         }
-#endif
         const unsigned c = __byte_perm(__float_as_uint(q2.z), 0u, band_sel);  // this band's byte
         if (c == kBandMiss) continue;  // warp-uniform
         const float4 q0 = list[3 * s + 0];
@@ -272,7 +208,7 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
         const f2_t QY = pack2(dy, dy + 1.0f);
         const f2_t CQ2 = bcast2(q1.x), T12 = bcast2(t1), T02 = bcast2(t0);
         const f2_t R2 = bcast2(q1.z), G2 = bcast2(q1.w), B2 = bcast2(q2.x);
-        if (c == kBandFull) {
+        if (c == kBandFull && q2.w >= 0.0f) {
             const f2_t E = fma2(fma2(CQ2, QY, T12), QY, T02);
             const float c4 = 4.0f * q1.x;
             const f2_t D = fma2(bcast2(c4), QY, bcast2(fmaf(2.0f, t1, c4)));  // e(i+2) - e(i)
@@ -283,17 +219,16 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
             f2_t G = pack2(ex2_approx(d0), ex2_approx(d1));
             const f2_t H2 = bcast2(q2.w);
             if (kStats) work[0] += kPairs;
-            GGS_PX_BLEND(0, F)
-            mul2_acc(F, G);
-            mul2_acc(G, H2);
-            GGS_PX_BLEND(1, F)
-            mul2_acc(F, G);
-            mul2_acc(G, H2);
-            GGS_PX_BLEND(2, F)
-            mul2_acc(F, G);
-            GGS_PX_BLEND(3, F)
+#define GGS_RECUR_PAIR(k)                    \
+    GGS_PX_BLEND(k, F)                       \
+    if (k + 1 < kPairs) {                    \
+        mul2_acc(F, G);                      \
+        if (k + 2 < kPairs) mul2_acc(G, H2); \
+    }
+            GGS_PAIRS(GGS_RECUR_PAIR)
+#undef GGS_RECUR_PAIR
         } else {
-            const int lo = (int)(c & 7u), hi = (int)(c >> 4);
+            const int lo = (int)(c & 15u), hi = (int)(c >> 4);
 #define GGS_EXACT_PAIR(k)                                                          \
     if (2 * k + 1 >= lo && 2 * k <= hi) {                                          \
         const f2_t QYk = add2(QY, bcast2((float)(2 * k)));                         \
@@ -306,10 +241,7 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
         if (kStats) work[1] += 1;                                                  \
         GGS_PX_BLEND(k, F)                                                         \
     }
-            GGS_EXACT_PAIR(0)
-            GGS_EXACT_PAIR(1)
-            GGS_EXACT_PAIR(2)
-            GGS_EXACT_PAIR(3)
+            GGS_PAIRS(GGS_EXACT_PAIR)
 #undef GGS_EXACT_PAIR
         }
     }
@@ -338,33 +270,19 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
     const int X0 = tx * kTileW, Y0 = ty * kTileH;
     const int X1 = X0 + kTileW - 1, Y1 = Y0 + kTileH - 1;
     const int X = X0 + lane, Yb = Y0 + warp * kRowsPerThread;
-#if GGS_PIN_CONSTS >= 2
-    const float Xf = __shfl_sync(0xffffffffu, (float)X, lane);   // pinned like lanebit below
+    // Loop constants of the composite, pinned in registers by a (no-op) shuffle.
+    const float Xf = __shfl_sync(0xffffffffu, (float)X, lane);
     const float Ybf = __shfl_sync(0xffffffffu, (float)Yb, lane);
-#else
-    const float Xf = (float)X, Ybf = (float)Yb;
-#endif
-#if GGS_PIN_CONSTS
-    // Routed through a shuffle so ptxas cannot rematerialise them from %tid.x inside the
-    // composite loop (it otherwise re-reads the special register once per list entry).
     const unsigned lanebit = __shfl_sync(0xffffffffu, 1u << lane, lane);
-    const unsigned band_sel = __shfl_sync(0xffffffffu, 0x4440u + (unsigned)warp, lane);
-#else
-    const unsigned lanebit = 1u << lane;
-    const unsigned band_sel = 0x4440u + (unsigned)warp;  // PRMT: byte `warp`, zero-extended
-#endif
+    const unsigned band_sel = __shfl_sync(0xffffffffu, 0x4440u + (unsigned)warp, lane);  // PRMT: byte `warp`
 
     // Transmittance starts at 1 inside the image and at 0 outside it: pixels beyond the image
     // edge then take no colour and never keep a band from saturating.
-    Pixels px;
     GGS_PX_DECLARE();
 #define GGS_T_INIT(k)                                              \
     GGS_PX_INIT(k, (X < W && Yb + 2 * k < H) ? 1.0f : 0.0f,        \
                 (X < W && Yb + 2 * k + 1 < H) ? 1.0f : 0.0f)
-    GGS_T_INIT(0);
-    GGS_T_INIT(1);
-    GGS_T_INIT(2);
-    GGS_T_INIT(3);
+    GGS_PAIRS(GGS_T_INIT)
 #undef GGS_T_INIT
     bool live = true;  // warp-uniform: this band still has a non-opaque pixel
 
@@ -411,29 +329,21 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
                 const int pos = run + pre + __popc(bal[j] & (lanebit - 1u));
                 const float4 *src = recb + (int64_t)idx[j] * 3;
                 float4 q2 = __ldg(src + 2);
-                const bool steep = q2.w < 0.0f;
                 q2.y = __uint_as_float(lane_mask(bx0[j], bx1[j], X0));
-                q2.z = __uint_as_float(row_code(by0[j], by1[j], Y0, steep));
-#if GGS_CP_ASYNC
+                q2.z = __uint_as_float(row_code(by0[j], by1[j], Y0));
                 cp_async16(&s_list[pos * 3 + 0], src + 0);  // LDGSTS: no register staging
                 cp_async16(&s_list[pos * 3 + 1], src + 1);
-#else
-                s_list[pos * 3 + 0] = __ldg(src + 0);
-                s_list[pos * 3 + 1] = __ldg(src + 1);
-#endif
                 s_list[pos * 3 + 2] = q2;
             }
             run += tot;
         }
         cnt = run;
-#if GGS_CP_ASYNC
         cp_async_wait_all();
-#endif
         __syncthreads();
         if (cnt > kListCap - kScanChunk || top <= kScanChunk) {
-            if (live) live = composite_list<kStats>(s_list, cnt, lanebit, band_sel, Xf, Ybf, px, work);
+            if (live) live = composite_list<kStats>(s_list, cnt, lanebit, band_sel, Xf, Ybf, work);
             cnt = 0;
-            // all four bands opaque: the rest of the genome is hidden behind what is drawn
+            // every band opaque: the rest of the genome is hidden behind what is drawn
             if (__syncthreads_and(!live)) break;
         }
     }
@@ -443,10 +353,9 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
     float num = 0.0f, den = 0.0f;
     const bool want_fit = (target != nullptr);
     float prr[kPairs][2], pgg[kPairs][2], pbb[kPairs][2], ptt[kPairs][2];
-    GGS_PX_READ(0, prr[0], pgg[0], pbb[0], ptt[0]);
-    GGS_PX_READ(1, prr[1], pgg[1], pbb[1], ptt[1]);
-    GGS_PX_READ(2, prr[2], pgg[2], pbb[2], ptt[2]);
-    GGS_PX_READ(3, prr[3], pgg[3], pbb[3], ptt[3]);
+#define GGS_READ_ALL(k) GGS_PX_READ(k, prr[k], pgg[k], pbb[k], ptt[k])
+    GGS_PAIRS(GGS_READ_ALL)
+#undef GGS_READ_ALL
 #pragma unroll
     for (int i = 0; i < kRowsPerThread; ++i) {
         const int Y = Yb + i;
