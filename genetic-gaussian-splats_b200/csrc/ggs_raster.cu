@@ -49,7 +49,13 @@ namespace {
 constexpr int kPairs = kRowsPerThread / 2;
 constexpr int kScanPerThread = 256 / kThreads;          // 256 records examined per round
 constexpr int kScanChunk = kThreads * kScanPerThread;
-constexpr int kSatEvery = 8;                             // list entries between saturation votes
+#ifndef GGS_SAT_EVERY
+#define GGS_SAT_EVERY 8
+#endif
+#ifndef GGS_BOX_PREFETCH
+#define GGS_BOX_PREFETCH 1
+#endif
+constexpr int kSatEvery = GGS_SAT_EVERY;                 // list entries between saturation votes
 constexpr float kOpaque = 2.384185791015625e-07f;        // 2^-22: transmittance counted as zero
 static_assert(kScanPerThread >= 1, "at most 256 threads per CTA");
 
@@ -97,33 +103,34 @@ __device__ __forceinline__ f2_t add2(f2_t a, f2_t b)
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-__device__ __forceinline__ void mul2_acc(f2_t &c, f2_t a)  // c *= a
-{
-    asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(c) : "l"(a));
-}
 
 // ---- pixel state: named PTX registers ggs_{r,g,b,t}<pair> -------------------------------------
 // Pair k of a thread holds rows (2k, 2k+1) of its column: accumulated colour (premultiplied,
 // front to back) and transmittance.  GGS_PAIRS(M) expands M(0) ... M(kPairs-1).
 #if GGS_ROWS == 8
-#define GGS_PX_DECLARE() asm volatile(".reg .b64 ggs_r<4>, ggs_g<4>, ggs_b<4>, ggs_t<4>;")
+#define GGS_PX_DECLARE() asm volatile(".reg .b64 ggs_r<4>, ggs_g<4>, ggs_b<4>, ggs_t<4>, ggs_F, ggs_G;")
 #define GGS_PAIRS(M) M(0) M(1) M(2) M(3)
 #else
-#define GGS_PX_DECLARE() asm volatile(".reg .b64 ggs_r<8>, ggs_g<8>, ggs_b<8>, ggs_t<8>;")
+#define GGS_PX_DECLARE() asm volatile(".reg .b64 ggs_r<8>, ggs_g<8>, ggs_b<8>, ggs_t<8>, ggs_F, ggs_G;")
 #define GGS_PAIRS(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
 #endif
 #define GGS_PX_INIT(k, ta_, tb_)                                                          \
     asm volatile("mov.b64 ggs_r" #k ", 0;\n\tmov.b64 ggs_g" #k ", 0;\n\tmov.b64 ggs_b" #k   \
                  ", 0;\n\tmov.b64 ggs_t" #k ", {%0, %1};" ::"f"(ta_), "f"(tb_));
+// The falloff pair of the current rows (ggs_F) and its stride-2 ratio (ggs_G) are named too.
+#define GGS_SET_F(f0_, f1_) asm volatile("mov.b64 ggs_F, {%0, %1};" ::"f"(f0_), "f"(f1_));
+#define GGS_SET_G(g0_, g1_) asm volatile("mov.b64 ggs_G, {%0, %1};" ::"f"(g0_), "f"(g1_));
+#define GGS_STEP_F() asm volatile("mul.rn.f32x2 ggs_F, ggs_F, ggs_G;");
+#define GGS_STEP_G(H_) asm volatile("mul.rn.f32x2 ggs_G, ggs_G, %0;" ::"l"(H_));
 // One row pair, front to back (render.py:194-196 rearranged): W = F*T, C += W*col, T -= W.
-#define GGS_PX_BLEND(k, F_)                                                               \
+#define GGS_PX_BLEND(k)                                                                   \
     asm volatile("{\n\t.reg .b64 w;\n\t"                                                 \
-                 "mul.rn.f32x2 w, %0, ggs_t" #k ";\n\t"                                   \
-                 "fma.rn.f32x2 ggs_r" #k ", w, %1, ggs_r" #k ";\n\t"                      \
-                 "fma.rn.f32x2 ggs_g" #k ", w, %2, ggs_g" #k ";\n\t"                      \
-                 "fma.rn.f32x2 ggs_b" #k ", w, %3, ggs_b" #k ";\n\t"                      \
-                 "sub.rn.f32x2 ggs_t" #k ", ggs_t" #k ", w;\n\t}" ::"l"(F_),              \
-                 "l"(R2), "l"(G2), "l"(B2));
+                 "mul.rn.f32x2 w, ggs_F, ggs_t" #k ";\n\t"                                \
+                 "fma.rn.f32x2 ggs_r" #k ", w, %0, ggs_r" #k ";\n\t"                      \
+                 "fma.rn.f32x2 ggs_g" #k ", w, %1, ggs_g" #k ";\n\t"                      \
+                 "fma.rn.f32x2 ggs_b" #k ", w, %2, ggs_b" #k ";\n\t"                      \
+                 "sub.rn.f32x2 ggs_t" #k ", ggs_t" #k ", w;\n\t}" ::"l"(R2), "l"(G2),    \
+                 "l"(B2));
 #define GGS_PX_READ_T(k, a_, b_) asm volatile("mov.b64 {%0, %1}, ggs_t" #k ";" : "=f"(a_), "=f"(b_));
 #define GGS_PX_READ(k, r_, g_, b_, t_)                                                    \
     asm volatile("mov.b64 {%0, %1}, ggs_r" #k ";\n\tmov.b64 {%2, %3}, ggs_g" #k            \
@@ -215,15 +222,15 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
             float e0, e1, d0, d1;
             unpack2(E, e0, e1);
             unpack2(D, d0, d1);
-            f2_t F = pack2(ex2_approx(e0), ex2_approx(e1));
-            f2_t G = pack2(ex2_approx(d0), ex2_approx(d1));
+            GGS_SET_F(ex2_approx(e0), ex2_approx(e1))
+            GGS_SET_G(ex2_approx(d0), ex2_approx(d1))
             const f2_t H2 = bcast2(q2.w);
             if (kStats) work[0] += kPairs;
 #define GGS_RECUR_PAIR(k)                    \
-    GGS_PX_BLEND(k, F)                       \
+    GGS_PX_BLEND(k)                          \
     if (k + 1 < kPairs) {                    \
-        mul2_acc(F, G);                      \
-        if (k + 2 < kPairs) mul2_acc(G, H2); \
+        GGS_STEP_F()                         \
+        if (k + 2 < kPairs) GGS_STEP_G(H2)   \
     }
             GGS_PAIRS(GGS_RECUR_PAIR)
 #undef GGS_RECUR_PAIR
@@ -237,9 +244,9 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
         unpack2(E, e0, e1);                                                        \
         const float f0 = (2 * k >= lo) ? ex2_approx(e0) : 0.0f;                    \
         const float f1 = (2 * k + 1 <= hi) ? ex2_approx(e1) : 0.0f;                \
-        const f2_t F = pack2(f0, f1);                                              \
+        GGS_SET_F(f0, f1)                                                          \
         if (kStats) work[1] += 1;                                                  \
-        GGS_PX_BLEND(k, F)                                                         \
+        GGS_PX_BLEND(k)                                                            \
     }
             GGS_PAIRS(GGS_EXACT_PAIR)
 #undef GGS_EXACT_PAIR
@@ -293,6 +300,14 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
     // maps thread `tid` to record  top - 1 - (j*kThreads + tid): ascending (j, tid) is
     // descending genome order, so the ordinary ballot compaction yields the order we need.
     int cnt = 0;
+#if GGS_BOX_PREFETCH
+    uint2 nbox[kScanPerThread];  // the round's boxes, loaded one round ahead
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j) {
+        const int i0 = N - 1 - (j * kThreads + tid);
+        nbox[j] = (i0 >= 0) ? __ldg(boxb + i0) : make_uint2(0xffff7fffu, 0xffff7fffu);
+    }
+#endif
     for (int top = N; top > 0; top -= kScanChunk) {
         bool hit[kScanPerThread];
         unsigned bal[kScanPerThread];
@@ -301,10 +316,15 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
 #pragma unroll
         for (int j = 0; j < kScanPerThread; ++j) {
             idx[j] = top - 1 - (j * kThreads + tid);
+#if GGS_BOX_PREFETCH
+            const uint2 box = nbox[j];
+            {
+#else
             hit[j] = false;
             bx0[j] = bx1[j] = by0[j] = by1[j] = 0;
             if (idx[j] >= 0) {
                 const uint2 box = __ldg(boxb + idx[j]);
+#endif
                 bx0[j] = (int)(short)(box.x & 0xffff);
                 bx1[j] = (int)box.x >> 16;
                 by0[j] = (int)(short)(box.y & 0xffff);
@@ -314,6 +334,13 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
             bal[j] = __ballot_sync(0xffffffffu, hit[j]);
             if (lane == 0) s_wcnt[j][warp] = __popc(bal[j]);
         }
+#if GGS_BOX_PREFETCH
+#pragma unroll
+        for (int j = 0; j < kScanPerThread; ++j) {
+            const int i1 = top - kScanChunk - 1 - (j * kThreads + tid);
+            nbox[j] = (i1 >= 0) ? __ldg(boxb + i1) : make_uint2(0xffff7fffu, 0xffff7fffu);
+        }
+#endif
         __syncthreads();
         int run = cnt;
 #pragma unroll
