@@ -489,3 +489,26 @@ def test_randomised_shapes_against_oracle(ggs):
             np.testing.assert_allclose(f, f_ref, rtol=FIT_RTOL, err_msg=str((trial, H, W, N, B, k, list(kw))))
     print(f"AABB flips over the fuzz set: {n_flips}")
     assert n_flips <= 2
+
+
+def test_non_finite_genes_do_not_leak_into_other_candidates(ggs):
+    """NaN / inf / huge genes make that candidate's own result meaningless (as in the
+    reference) but must neither fault nor disturb the rest of the batch."""
+    from ggs_b200 import synth
+    B, N, H, W = 6, 90, 96, 128
+    g = synth.new_population_np(B, N, H, W, seed=77)
+    t = cuda(synth.synthetic_target_np(H, W, 77))
+    clean = ggs.fitness(cuda(g), t, H, W, 3.0)
+    bad = g.copy()
+    bad[1, 3, :] = np.nan
+    bad[1, 7, 2:5] = [np.inf, -np.inf, 1e30]
+    bad[3, 0, 0:2] = [np.inf, -np.inf]
+    bad[3, 5, 4] = 1e20            # absurd off-diagonal term
+    bad[3, 9, 2:4] = [80.0, 80.0]  # exp overflow
+    out = ggs.fitness(cuda(bad), t, H, W, 3.0)
+    torch.cuda.synchronize()
+    for b in (0, 2, 4, 5):
+        assert out[b].item() == clean[b].item()
+    img = ggs.render(ggs.encode(cuda(bad)), H, W, 3.0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(img[[0, 2, 4, 5]]).all()
