@@ -1,21 +1,22 @@
-"""Work-size helpers (reference: modules/resize.py:6-20).  One-time host-side scalar maths."""
+"""Work-size helpers, host-side scalar maths run once per run (reference: modules/resize.py:6-20)."""
+import math
 from typing import Tuple
 
-import numpy as np
 import torch
 
 
 def choose_work_size(Ht: int, Wt: int, max_side: int = 128) -> Tuple[int, int]:
-    """Scale (Ht, Wt) so the longer side equals max_side, keeping the aspect ratio."""
-    if Ht >= Wt:
-        return max_side, max(1, int(round(Wt * max_side / Ht)))
-    return max(1, int(round(Ht * max_side / Wt))), max_side
+    """(H, W) with the longer side equal to max_side and the aspect ratio of (Ht, Wt)."""
+    long_side, short_side = max(Ht, Wt), min(Ht, Wt)
+    short = max(1, int(round(short_side * max_side / long_side)))
+    return (max_side, short) if Ht >= Wt else (short, max_side)
 
 
 def scale_genome_pixels_anisotropic(ind: torch.Tensor, sH: float, sW: float) -> torch.Tensor:
-    """Rescale the pixel-space sigmas of an axes-angle genome for a render at another size:
-    log sigma_x += log sW, log sigma_y += log sH (positions are already relative)."""
-    out = ind.clone()
-    out[:, 2] += float(np.log(sW))
-    out[:, 3] += float(np.log(sH))
-    return out
+    """Copy of an axes-angle genome whose pixel-space sigmas are rescaled for a render at
+    another size: log sigma_x gains log sW, log sigma_y gains log sH; positions are relative
+    already."""
+    scaled = ind.clone()
+    scaled[:, 2].add_(math.log(sW))
+    scaled[:, 3].add_(math.log(sH))
+    return scaled
