@@ -186,7 +186,7 @@ def run_reference(args, wl):
     from oracle import oracle
     oracle.build()
     cores = oracle.threads()
-    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    per_step = max(0.5, min(20.0, 120.0 / max(1, args.steps + args.warmup)))  # ~2 min in all
     for _ in range(args.warmup):
         cpu_sample(wl, per_step / 4)
     vals, n_last, t_total = [], 0, 0.0
@@ -387,7 +387,7 @@ def run_ours(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c3")
