@@ -25,8 +25,9 @@ from modules.fitness import fitness_many
 from modules.genetic import mutate_population
 from modules.mask import compute_importance_mask
 from modules.population import new_individual
-from modules.utils import (_anneal_factor, prewarm_renderer, save_curves_csv, save_frame_png,
-                           save_loss_curve_png)
+from ggs_b200 import breed
+from modules.utils import (_anneal_factor, build_mut_sigma, prewarm_renderer, save_curves_csv,
+                           save_frame_png, save_loss_curve_png, scale_log_bounds)
 
 _ensure_hw = prepare_target  # the reference's private name (annealing.py:19-26)
 
@@ -85,8 +86,21 @@ def simulated_annealing(
         return fitness_many(batch, target, H, W, k_sigma, device, tile=32, weight_mask=imp_mask,
                             boost_only=boost_only).cpu().tolist()
 
+    run_seed = int(torch.randint(0, 2**31 - 1, (1,)).item())  # follows torch.manual_seed
+    draws = [0]
+
     def propose(state: torch.Tensor, count: int, it: int) -> torch.Tensor:
+        """`count` independently mutated copies of `state` (annealing.py:121-128, batched)."""
         nb = state.unsqueeze(0).repeat(count, 1, 1)
+        if nb.is_cuda:
+            # one launch: the GA breeding kernel with identical parents and no crossover is
+            # exactly `count` independent mutate_individual calls
+            draws[0] += 1
+            sigma = build_mut_sigma(it, iterations, sigma_schedule, mut_sigma_max, mut_sigma_min)
+            lo, hi = scale_log_bounds(H, W, min_scale_splats, max_scale_splats)
+            return breed(nb, torch.zeros(count, device=nb.device), sigma, tour_k=1, cxpb=0.0,
+                         mutpb=mutpb, log_scale_lo=lo, log_scale_hi=hi, seed=run_seed,
+                         generation=draws[0])
         return mutate_population(nb, it, iterations, sigma_schedule, mut_sigma_max, mut_sigma_min,
                                  mutpb, H, W, min_scale_splats, max_scale_splats)
 
