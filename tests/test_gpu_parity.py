@@ -459,8 +459,10 @@ def test_randomised_shapes_against_oracle(ggs):
     """Seeded fuzz over image sizes, splat counts, k_sigma, layouts, backgrounds and modes."""
     from ggs_b200 import synth
     rng = np.random.default_rng(2024)
-    n_flips = 0
-    for trial in range(24):
+    n_flips = n_undefined = 0
+    import os
+    trials = int(os.environ.get("GGS_FUZZ_TRIALS", "24"))   # raise for a soak run
+    for trial in range(trials):
         H, W = int(rng.integers(1, 180)), int(rng.integers(1, 180))
         N, B = int(rng.integers(0, 260)), int(rng.integers(1, 5))
         k = float(rng.choice([1.0, 2.0, 3.0, 4.5]))
@@ -481,14 +483,37 @@ def test_randomised_shapes_against_oracle(ggs):
             continue                                  # counted, reported below, not hidden
         img_ref = oracle.render(chol, H, W, k, background=bg)
         img = ggs.render(cuda(chol), H, W, k, background=bg).cpu().numpy()
-        assert np.abs(img - img_ref).max() <= IMG_TOL, (trial, H, W, N, B, k)
+        # A needle splat (sigma of a few hundredths of a pixel, lying along a diagonal) makes the
+        # three terms of the reference's quadratic form cancel by six or more orders of
+        # magnitude.  Two things follow, both in the reference arithmetic itself:
+        #  * the sum can come out hugely negative, exp overflows and the blend is inf - inf = NaN;
+        #  * short of that, the image depends on the last bit of exp(log sigma): moving the two
+        #    log-sigma genes by ONE ulp moves the reference's own image by more than the
+        #    tolerance (the reference under the Triton interpreter, torch.exp on the CPU, and the
+        #    reference on a GPU, CUDA expf, differ by exactly such bits).
+        # Such candidates have no result to be on a par with.  Only a candidate that misses the
+        # tolerance is tested for this, and it must show the sensitivity to be excused.
+        with np.errstate(invalid="ignore"):
+            err = np.abs(img - img_ref).reshape(B, -1).max(axis=1, initial=0.0)
+        defined = np.isfinite(img_ref).reshape(B, -1).all(axis=1) & (err <= IMG_TOL)
+        if not defined.all():
+            nudged = chol.copy()
+            nudged[..., 2:4] = np.nextafter(nudged[..., 2:4], np.float32(np.inf))
+            with np.errstate(invalid="ignore"):
+                drift = np.abs(oracle.render(nudged, H, W, k, background=bg) - img_ref)
+            drift = drift.reshape(B, -1).max(axis=1, initial=0.0)
+            excused = ~np.isfinite(drift) | (drift > 0.5 * IMG_TOL)
+            assert (defined | excused).all(), (trial, H, W, N, B, k, err, drift)
+        n_undefined += int((~defined).sum())
         for kw in ({}, {"weight_mask": m}, {"weight_mask": m, "boost_only": True}):
             f_ref = oracle.fitness(g, t, H, W, k, **kw)
             kw_gpu = {a: (cuda(v) if isinstance(v, np.ndarray) else v) for a, v in kw.items()}
             f = ggs.fitness(cuda(g), cuda(t), H, W, k, **kw_gpu).cpu().numpy()
-            np.testing.assert_allclose(f, f_ref, rtol=FIT_RTOL, err_msg=str((trial, H, W, N, B, k, list(kw))))
-    print(f"AABB flips over the fuzz set: {n_flips}")
-    assert n_flips <= 2
+            np.testing.assert_allclose(f[defined], f_ref[defined], rtol=FIT_RTOL,
+                                       err_msg=str((trial, H, W, N, B, k, list(kw))))
+    print(f"AABB flips over the fuzz set: {n_flips}; candidates undefined in the reference: {n_undefined}")
+    assert n_flips <= max(2, trials // 50)
+    assert n_undefined <= max(1, trials // 20)
 
 
 def test_non_finite_genes_do_not_leak_into_other_candidates(ggs):
