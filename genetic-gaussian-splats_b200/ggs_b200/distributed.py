@@ -18,6 +18,31 @@ import torch
 import torch.distributed as dist
 
 
+def init_from_env() -> Tuple[int, int]:
+    """(rank, world) of this process.  Under `torchrun` (WORLD_SIZE > 1 in the environment) the
+    process binds to cuda:LOCAL_RANK and joins the NCCL group on first use, so the reference's
+    run scripts shard a GA run over the GPUs of a box without any change:
+        torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 run_ggs.py
+    GGS_B200_NO_SHARD=1 keeps a process on its own (every rank then runs the whole job)."""
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1 or os.environ.get("GGS_B200_NO_SHARD", "0") == "1":
+        return 0, 1
+    if not dist.is_initialized():
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank(), dist.get_world_size()
+
+
+def replicate(t: torch.Tensor, src: int = 0, group=None) -> torch.Tensor:
+    """Rank `src`'s copy of `t` on every rank (in place): makes the state that replicated
+    deterministic breeding starts from identical even when the ranks' RNGs were not seeded alike."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(t, src=src, group=group)
+    return t
+
+
 def shard_bounds(total: int, world: int, rank: int) -> Tuple[int, int]:
     """Contiguous split of `total` items; the first `total % world` ranks get one extra."""
     assert world >= 1 and 0 <= rank < world and total >= 0

@@ -2,7 +2,11 @@
 return value, restructured around a population tensor that stays resident on the device:
 selection, crossover and mutation are one CUDA launch (ggs_ga_breed via modules/genetic.py),
 elitism is a row copy, the evaluation is the fused CUDA path, and the only host transfer per generation is the fitness
-vector.  Two reference quirks are dropped because they cannot change results: elites are not
+vector.  Launched under torchrun the same function shards the evaluation over the ranks
+(BASELINE config 4): every rank holds the whole population and breeds the same next generation
+from the same counter-based random stream, evaluates its contiguous slice, and one NCCL
+all-gather moves the fitness vector; rank 0 alone writes frames and curves.
+Two reference quirks are dropped because they cannot change results: elites are not
 re-evaluated (the evaluation is deterministic, algorithm.py:134) -- their stored fitness is
 reused -- and the offspring that elitism would discard are still evaluated (one launch)."""
 from statistics import median
@@ -21,6 +25,7 @@ from modules.fitness import fitness_many
 from modules.genetic import breed_population
 from modules.mask import compute_importance_mask
 from modules.population import new_population
+from ggs_b200.distributed import ShardedEvaluator, init_from_env, replicate
 from modules.utils import (_anneal_factor, prewarm_renderer, save_curves_csv, save_frame_png,
                            save_loss_curve_png)
 
@@ -49,6 +54,9 @@ def genetic_approx(target_img_uint8: torch.Tensor,
                    loss_png_path: str = "",
                    loss_csv_path: str = "",
                    loss_log_y: bool = False) -> Tuple[torch.Tensor, float]:
+    rank, world = init_from_env()      # (0, 1) unless launched under torchrun
+    if rank != 0:                      # one writer
+        save_video, loss_png_path, loss_csv_path = False, "", ""
     t = prepare_target(target_img_uint8, H, W)
     imp_mask = compute_importance_mask(t, H, W, edge_scales=(1, 2, 4), w_edge=0.7, w_var=0.3,
                                        gamma=0.7, floor=0.15, smooth=3,
@@ -56,11 +64,17 @@ def genetic_approx(target_img_uint8: torch.Tensor,
     target = t.to(device)          # target and mask stay resident for the whole run
     prewarm_renderer(H, W, k_sigma, device)
 
-    def evaluate(pop_tensor: torch.Tensor) -> torch.Tensor:
-        return fitness_many(pop_tensor, target, H, W, k_sigma, device, tile=32,
-                            weight_mask=imp_mask, boost_only=boost_only)
+    if world > 1:
+        sharded = ShardedEvaluator(target, H, W, k_sigma, weight_mask=imp_mask,
+                                   boost_only=boost_only, device=target.device)
+        evaluate = sharded.fitness     # this rank's slice + all-gather: the full vector everywhere
+    else:
+        def evaluate(pop_tensor: torch.Tensor) -> torch.Tensor:
+            return fitness_many(pop_tensor, target, H, W, k_sigma, device, tile=32,
+                                weight_mask=imp_mask, boost_only=boost_only)
 
-    pop = new_population(pop_size, n_splats, H, W, min_scale_splats, max_scale_splats, device=device)
+    pop = replicate(new_population(pop_size, n_splats, H, W, min_scale_splats, max_scale_splats,
+                                   device=device))
     fit = evaluate(pop)
     fit_host = fit.cpu().tolist()
 
@@ -75,8 +89,9 @@ def genetic_approx(target_img_uint8: torch.Tensor,
         save_frame_png(0, best_ind, pad, prefix, video_dir, H, W, k_sigma, device, save_video)
 
     n_elite = max(1, elite_k)
-    run_seed = int(torch.randint(0, 2**31 - 1, (1,)).item())  # follows torch.manual_seed
-    pbar = tqdm(range(1, generations + 1), desc="GA generations", leave=True)
+    run_seed = int(replicate(torch.randint(0, 2**31 - 1, (1,)).to(device)).item())  # follows torch.manual_seed
+    pbar = tqdm(range(1, generations + 1), desc="GA generations", leave=True,
+                **({"disable": True} if rank != 0 else {}))
     try:
         for gen in pbar:
             # selection -> crossover -> mutation: one launch on the resident tensor

@@ -117,6 +117,53 @@ def test_two_gpu_nccl_gather_is_bit_identical(cuda_ok, tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+GA_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+os.environ["TQDM_DISABLE"] = "1"
+root = sys.argv[1]
+sys.path[:0] = [root, os.path.join(root, "genetic-gaussian-splats_b200")]
+import modules.config as C
+from modules.algorithm import genetic_approx
+from ggs_b200 import synth
+H, W = 64, 96
+target = torch.from_numpy(synth.synthetic_target_np(H, W, 9))
+kw = dict(H=H, W=W, device="cuda", pop_size=22, n_splats=40, generations=15, tour_k=C.TOUR_K,
+          elite_k=C.ELITE_K, cxpb=C.CXPB, mutpb=C.MUTPB, mut_sigma_max=C.MUT_SIGMA_MAX,
+          mut_sigma_min=C.MUT_SIGMA_MIN, schedule=C.SCHEDULE, min_scale_splats=C.MIN_SCALE_SPLATS,
+          max_scale_splats=C.MAX_SCALE_SPLATS, k_sigma=C.K_SIGMA, mask_strength=C.MASK_STRENGTH,
+          boost_only=C.BOOST_ONLY)
+torch.manual_seed(5 + int(os.environ["RANK"]))      # ranks seeded DIFFERENTLY on purpose
+best_s, fit_s = genetic_approx(target, **kw)        # sharded over the ranks (torchrun env)
+assert dist.is_initialized() and dist.get_world_size() == int(os.environ["WORLD_SIZE"])
+# every rank must hold the same result ...
+probe = torch.cat([best_s.flatten().double(), torch.tensor([fit_s], dtype=torch.float64)]).cuda()
+lo, hi = probe.clone(), probe.clone()
+dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+same = bool(torch.equal(lo, hi))
+# ... and it must be the single-GPU run of rank 0's seed, bit for bit
+os.environ["GGS_B200_NO_SHARD"] = "1"
+torch.manual_seed(5)
+best_1, fit_1 = genetic_approx(target, **kw)
+ok = same and fit_1 == fit_s and torch.equal(best_1, best_s)
+flag = torch.tensor([1 if ok else 0]).cuda()
+dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+dist.destroy_process_group()
+sys.exit(0 if int(flag) == 1 else 3)
+'''
+
+
+def test_two_gpu_sharded_ga_equals_single_gpu_run(cuda_ok, tmp_path):
+    """torchrun + the unchanged GA entry point: replicated breeding, sharded evaluation."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "ga_worker.py"
+    script.write_text(GA_WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29654", str(script), ROOT]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_run_ggs_flow_end_to_end(cuda_ok, tmp_path):
     """The flow of run_ggs.py:31-77 with its outputs: load an image file, choose the work size,
     run the GA with frames and loss curves, rescale the best genome and render it at full size."""
