@@ -1,15 +1,15 @@
 """Genetic-algorithm loop (reference: modules/algorithm.py:17-195), same entry point and
 return value, restructured around a population tensor that stays resident on the device:
 selection, crossover and mutation are one CUDA launch (ggs_ga_breed via modules/genetic.py),
-elitism is a row copy, the evaluation is the fused CUDA path, and the only host transfer per generation is the fitness
-vector.  Launched under torchrun the same function shards the evaluation over the ranks
-(BASELINE config 4): every rank holds the whole population and breeds the same next generation
-from the same counter-based random stream, evaluates its contiguous slice, and one NCCL
-all-gather moves the fitness vector; rank 0 alone writes frames and curves.
+elitism is a row copy, the evaluation is the fused CUDA path, and the only host transfer per
+generation is three statistics of the fitness vector.  Launched under torchrun the same
+function shards the evaluation over the ranks (BASELINE config 4): every rank holds the whole
+population and breeds the same next generation from the same counter-based random stream,
+evaluates its contiguous slice, and one NCCL all-gather moves the fitness vector;
+rank 0 alone writes frames and curves.
 Two reference quirks are dropped because they cannot change results: elites are not
 re-evaluated (the evaluation is deterministic, algorithm.py:134) -- their stored fitness is
-reused -- and the offspring that elitism would discard are still evaluated (one launch)."""
-from statistics import median
+reused -- and the offspring that elitism discards are not evaluated at all."""
 from typing import Tuple
 
 import torch
@@ -76,45 +76,60 @@ def genetic_approx(target_img_uint8: torch.Tensor,
     pop = replicate(new_population(pop_size, n_splats, H, W, min_scale_splats, max_scale_splats,
                                    device=device))
     fit = evaluate(pop)
-    fit_host = fit.cpu().tolist()
 
-    best_idx = min(range(pop_size), key=fit_host.__getitem__)
-    best_ind, best_fit = pop[best_idx].clone(), fit_host[best_idx]
+    def summarise(fit_vec: torch.Tensor):
+        """(stable order, [best, mean, median] on the host): one small transfer per generation
+        instead of the whole fitness vector (statistics.median semantics: mean of the middle two)."""
+        order = torch.argsort(fit_vec, stable=True)
+        ranked = fit_vec[order].double()
+        n = ranked.shape[0]
+        stats = torch.stack([ranked[0], ranked.mean(), 0.5 * (ranked[(n - 1) // 2] + ranked[n // 2])])
+        return order, stats.tolist()
+
+    order, (best_fit, mean_fit, median_fit) = summarise(fit)
+    best_ind = pop[order[0]].clone()
     no_improve = 0
-    curves = {"best": [float(best_fit)], "mean": [sum(fit_host) / len(fit_host)],
-              "median": [float(median(fit_host))]}
+    curves = {"best": [best_fit], "mean": [mean_fit], "median": [median_fit]}
 
     pad = len(str(generations))
     if save_video:
         save_frame_png(0, best_ind, pad, prefix, video_dir, H, W, k_sigma, device, save_video)
 
     n_elite = max(1, elite_k)
+    keep = pop_size - n_elite
+    # Two generation buffers used alternately, each [n_elite + P, N, 9]: the breeding kernel writes
+    # the children behind the elite rows, so the next population (elites first, then the first
+    # `keep` children, algorithm.py:128-141) is a view of the buffer: no concatenation, no copy
+    # of the children.
+    room = [torch.empty((n_elite + pop_size, n_splats, 9), dtype=torch.float32, device=pop.device)
+            for _ in range(2)]
     run_seed = int(replicate(torch.randint(0, 2**31 - 1, (1,)).to(device)).item())  # follows torch.manual_seed
     pbar = tqdm(range(1, generations + 1), desc="GA generations", leave=True,
                 **({"disable": True} if rank != 0 else {}))
     try:
         for gen in pbar:
+            nxt = room[gen & 1]
             # selection -> crossover -> mutation: one launch on the resident tensor
-            offspring = breed_population(pop, fit, gen, generations, schedule, mut_sigma_max,
-                                         mut_sigma_min, tour_k, cxpb, mutpb, H, W,
-                                         min_scale_splats, max_scale_splats, seed=run_seed)
-            off_fit = evaluate(offspring)
+            children = breed_population(pop, fit, gen, generations, schedule, mut_sigma_max,
+                                        mut_sigma_min, tour_k, cxpb, mutpb, H, W,
+                                        min_scale_splats, max_scale_splats, seed=run_seed,
+                                        out=nxt[n_elite:])
+            off_fit = evaluate(children[:keep])
 
             # elitism: the n_elite best of the current generation survive unchanged
-            elite_idx = torch.argsort(fit, stable=True)[:n_elite]
-            keep = pop_size - n_elite
-            pop = torch.cat([pop[elite_idx], offspring[:keep]], dim=0)
-            fit = torch.cat([fit[elite_idx], off_fit[:keep]], dim=0)
-            fit_host = fit.cpu().tolist()
+            elite_idx = order[:n_elite]
+            nxt[:n_elite] = pop[elite_idx][..., :9]
+            fit = torch.cat([fit[elite_idx], off_fit], dim=0)
+            pop = nxt[:pop_size]
 
-            gbest = min(range(pop_size), key=fit_host.__getitem__)
-            if fit_host[gbest] + 1e-10 < best_fit:
-                best_fit, best_ind, no_improve = fit_host[gbest], pop[gbest].clone(), 0
+            order, (gen_best, mean_fit, median_fit) = summarise(fit)
+            if gen_best + 1e-10 < best_fit:
+                best_fit, best_ind, no_improve = gen_best, pop[order[0]].clone(), 0
             else:
                 no_improve += 1
-            curves["best"].append(float(best_fit))
-            curves["mean"].append(sum(fit_host) / len(fit_host))
-            curves["median"].append(float(median(fit_host)))
+            curves["best"].append(best_fit)
+            curves["mean"].append(mean_fit)
+            curves["median"].append(median_fit)
 
             if save_video and gen % max(1, frame_every) == 0:
                 save_frame_png(gen, best_ind, pad, prefix, video_dir, H, W, k_sigma, device, save_video)

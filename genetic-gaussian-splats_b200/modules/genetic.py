@@ -55,8 +55,9 @@ def mutate_individual(ind: torch.Tensor, is_elite: bool, gen: int, total_gens: i
 def breed_population(pop: torch.Tensor, fitness: torch.Tensor, gen: int, total_gens: int,
                      schedule: str, mut_sigma_max: dict, mut_sigma_min: dict, tour_k: int,
                      cxpb: float, mutpb: float, H: int, W: int, min_scale_splats: float,
-                     max_scale_splats: float, seed: int = 0) -> torch.Tensor:
-    """Selection + crossover + mutation of the whole population -> offspring [P,N,9].
+                     max_scale_splats: float, seed: int = 0, out=None) -> torch.Tensor:
+    """Selection + crossover + mutation of the whole population -> offspring [P,N,9]
+    (written into `out` when given: a contiguous [P,N,9] tensor that does not alias `pop`).
 
     On a CUDA population this is ONE kernel launch (ggs_ga_breed in libggs_b200.so, Philox
     counter-based randomness keyed by (seed, gen)); on a CPU population (tests) it is the
@@ -67,13 +68,17 @@ def breed_population(pop: torch.Tensor, fitness: torch.Tensor, gen: int, total_g
         lo, hi = scale_log_bounds(H, W, min_scale_splats, max_scale_splats)
         sigma = build_mut_sigma(gen, total_gens, schedule, mut_sigma_max, mut_sigma_min)
         return breed(pop, fitness, sigma, tour_k=tour_k, cxpb=cxpb, mutpb=mutpb, log_scale_lo=lo,
-                     log_scale_hi=hi, seed=seed, generation=gen)
+                     log_scale_hi=hi, seed=seed, generation=gen, out=out)
     P = pop.shape[0]
     parents = pop[tournament_indices(fitness, P, k=tour_k)]
     parents = parents[torch.randperm(P, device=pop.device)]
     offspring = crossover_population(parents[..., :9].contiguous(), cxpb)
-    return mutate_population(offspring, gen, total_gens, schedule, mut_sigma_max, mut_sigma_min,
-                             mutpb, H, W, min_scale_splats, max_scale_splats)
+    offspring = mutate_population(offspring, gen, total_gens, schedule, mut_sigma_max,
+                                  mut_sigma_min, mutpb, H, W, min_scale_splats, max_scale_splats)
+    if out is not None:
+        out.copy_(offspring)
+        return out
+    return offspring
 
 
 @torch.no_grad()
