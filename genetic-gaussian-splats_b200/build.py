@@ -30,6 +30,7 @@ SOURCES = {
     # keeps ptxas from renaming them out of place at any -O level; tests/test_cpu_sass.py guards it
     "ggs_raster.cu": [],
     "ggs_breed.cu": [],
+    "ggs_mask.cu": ["-fmad=false"],   # one rounding per operation, like the reference's torch ops
     "ggs_probe.cu": [],
     "ggs_api.cu": [],
 }

@@ -464,6 +464,49 @@ int ggs_ga_breed(const float *d_population, const float *d_fitness, int P, int N
     return GGS_OK;
 }
 
+size_t ggs_mask_workspace_bytes(int H, int W)
+{
+    if (H <= 0 || W <= 0) return 0;
+    return ggs::mask_workspace_bytes(H, W);
+}
+
+int ggs_importance_mask(const float *d_image, int H0, int W0, int H, int W, int image_is_0_255,
+                        const int *h_edge_scales, int n_scales, double w_edge, double w_var,
+                        double gamma, double floor, int smooth, double strength, float *d_mask,
+                        void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (H0 <= 0 || W0 <= 0 || H <= 0 || W <= 0 || H0 > GGS_MAX_SIDE || W0 > GGS_MAX_SIDE ||
+        H > GGS_MAX_SIDE || W > GGS_MAX_SIDE || n_scales < 0 || (n_scales > 0 && !h_edge_scales) ||
+        smooth < 0 || (smooth > 0 && (smooth & 1) == 0)) {
+        set_error("ggs_importance_mask: bad arguments (source %dx%d, work %dx%d, %d scales, "
+                  "smooth %d: must be 0 or odd)", H0, W0, H, W, n_scales, smooth);
+        return GGS_EINVAL;
+    }
+    for (int k = 0; k < n_scales; ++k) {
+        const int s = h_edge_scales[k];
+        if (s < 1 || s > H || s > W) {  // avg_pool2d would produce an empty map (mask.py:54)
+            set_error("ggs_importance_mask: edge scale %d does not fit a %dx%d image", s, H, W);
+            return GGS_EINVAL;
+        }
+    }
+    if (!d_image || !d_mask || !d_workspace) {
+        set_error("ggs_importance_mask: NULL buffer");
+        return GGS_EINVAL;
+    }
+    if (workspace_bytes < ggs::mask_workspace_bytes(H, W)) {
+        set_error("ggs_importance_mask: workspace of %zu bytes, %zu needed", workspace_bytes,
+                  ggs::mask_workspace_bytes(H, W));
+        return GGS_EWORKSPACE;
+    }
+    // Scalar arithmetic in double, then one rounding to float32: what Python + torch do.
+    GGS_CUDA(ggs::launch_importance_mask(
+        d_image, H0, W0, H, W, image_is_0_255 != 0, h_edge_scales, n_scales, (float)w_edge,
+        (float)w_var, (float)gamma, (float)(1.0 - floor), (float)floor, smooth,
+        (float)(1.0 - strength), (float)strength, strength < 1.0 ? 1 : 0, d_mask, d_workspace,
+        static_cast<cudaStream_t>(stream)));
+    return GGS_OK;
+}
+
 int ggs_stats_target(unsigned long long *d_counters2)
 {
     g_stats = d_counters2;

@@ -77,6 +77,13 @@ cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int 
                          const float sigma6[6], float log_lo, float log_hi, uint64_t seed,
                          uint32_t generation, cudaStream_t stream);
 
+size_t mask_workspace_bytes(int H, int W);
+cudaError_t launch_importance_mask(const float *d_image, int H0, int W0, int H, int W, int div255,
+                                   const int *scales, int n_scales, float w_edge, float w_var,
+                                   float gamma, float one_minus_floor, float floor_,
+                                   int smooth, float one_minus_strength, float strength,
+                                   int blend, float *d_mask, void *d_ws, cudaStream_t st);
+
 // probe.cu
 cudaError_t probe_peaks(float *h_out5);
 

@@ -180,6 +180,31 @@ def breed(population: torch.Tensor, fitness_values: torch.Tensor, sigma: dict, *
     return out
 
 
+def importance_mask(image: torch.Tensor, H: int, W: int, *, edge_scales=(1, 2, 4),
+                    w_edge: float = 0.7, w_var: float = 0.3, gamma: float = 0.7,
+                    floor: float = 0.15, smooth: int = 0, strength: float = 1.0) -> torch.Tensor:
+    """compute_importance_mask (mask.py:29-83) on the device: [H0,W0,3] image -> [H,W] weights
+    (ggs_importance_mask).  Same parameters and defaults as the reference."""
+    dev = _cuda_device(image.device)
+    img = _as_f32(image, dev)
+    assert img.ndim == 3 and img.shape[2] == 3, "image must be [H0, W0, 3]"
+    H0, W0 = int(img.shape[0]), int(img.shape[1])
+    H, W = int(H), int(W)
+    is255 = bool(img.max() > 1.5)                      # mask.py:45
+    scales = (ctypes.c_int * len(edge_scales))(*[int(s) for s in edge_scales])
+    out = torch.empty((H, W), dtype=torch.float32, device=dev)
+    need = lib().ggs_mask_workspace_bytes(H, W)
+    ws = torch.empty(max(int(need), 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().ggs_importance_mask(img.data_ptr(), H0, W0, H, W, int(is255), scales,
+                                        len(edge_scales), float(w_edge), float(w_var), float(gamma),
+                                        float(floor), int(smooth or 0), float(strength),
+                                        out.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)),
+              "ggs_importance_mask")
+    ws.record_stream(torch.cuda.current_stream(dev))
+    return out
+
+
 def count_evaluated_pairs(run, device=None) -> dict:
     """Run `run()` (any evaluation) on the instrumented raster kernel and return the number
     of (pixel, splat) pairs it actually evaluated, split by path."""

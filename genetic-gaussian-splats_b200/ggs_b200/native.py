@@ -20,6 +20,7 @@ _vp = ctypes.c_void_p
 _i = ctypes.c_int
 _i64 = ctypes.c_int64
 _f = ctypes.c_float
+_d = ctypes.c_double
 _sz = ctypes.c_size_t
 
 # name -> (restype, argtypes); one entry per symbol declared in include/ggs_b200.h
@@ -41,6 +42,9 @@ SIGNATURES = {
     "ggs_probe_peaks": (_i, [ctypes.POINTER(_f)]),
     "ggs_ga_breed": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _f, _f, ctypes.POINTER(_f), _f, _f,
                           ctypes.c_uint64, ctypes.c_uint32, _vp]),
+    "ggs_mask_workspace_bytes": (_sz, [_i, _i]),
+    "ggs_importance_mask": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.POINTER(_i), _i, _d, _d, _d, _d, _i,
+                                 _d, _vp, _vp, _sz, _vp]),
     "ggs_stats_target": (_i, [_vp]),
     "ggs_timing_enable": (_i, [_i]),
     "ggs_timing_read": (_i, [ctypes.POINTER(_f), ctypes.POINTER(_f), ctypes.POINTER(_i)]),

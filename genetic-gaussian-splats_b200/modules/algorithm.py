@@ -57,11 +57,10 @@ def genetic_approx(target_img_uint8: torch.Tensor,
     rank, world = init_from_env()      # (0, 1) unless launched under torchrun
     if rank != 0:                      # one writer
         save_video, loss_png_path, loss_csv_path = False, "", ""
-    t = prepare_target(target_img_uint8, H, W)
-    imp_mask = compute_importance_mask(t, H, W, edge_scales=(1, 2, 4), w_edge=0.7, w_var=0.3,
-                                       gamma=0.7, floor=0.15, smooth=3,
-                                       strength=mask_strength).to(device)
-    target = t.to(device)          # target and mask stay resident for the whole run
+    target = prepare_target(target_img_uint8, H, W).to(device)
+    # the mask is built on the device too (ggs_importance_mask); target and mask stay resident
+    imp_mask = compute_importance_mask(target, H, W, edge_scales=(1, 2, 4), w_edge=0.7, w_var=0.3,
+                                       gamma=0.7, floor=0.15, smooth=3, strength=mask_strength)
     prewarm_renderer(H, W, k_sigma, device)
 
     if world > 1:

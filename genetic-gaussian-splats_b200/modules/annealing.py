@@ -75,11 +75,9 @@ def simulated_annealing(
     batch_neighbors: bool = True,
 ) -> Tuple[torch.Tensor, float]:
     """Minimises the (masked) MSE energy; returns (best axes-angle individual on CPU, best MSE)."""
-    t = prepare_target(target_img_uint8, H, W)
-    target = t.to(device)
-    imp_mask = compute_importance_mask(t, H, W, edge_scales=(1, 2, 4), w_edge=0.7, w_var=0.3,
-                                       gamma=0.7, floor=0.15, smooth=3,
-                                       strength=mask_strength).to(device)
+    target = prepare_target(target_img_uint8, H, W).to(device)
+    imp_mask = compute_importance_mask(target, H, W, edge_scales=(1, 2, 4), w_edge=0.7, w_var=0.3,
+                                       gamma=0.7, floor=0.15, smooth=3, strength=mask_strength)
     prewarm_renderer(H, W, k_sigma, device)
 
     def energy(batch: torch.Tensor):

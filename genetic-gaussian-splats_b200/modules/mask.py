@@ -1,6 +1,9 @@
 """Importance (edge/detail) weight mask -- counterpart of the reference's modules/mask.py
-(compute_importance_mask, mask.py:29-83).  Runs once per run on whatever device the target is
-on; it is an *input* of the hot path, not part of it, so it stays plain torch."""
+(compute_importance_mask, mask.py:29-83), the `weight_mask` input of the fitness.  A target on
+a CUDA device goes through the library (ggs_importance_mask: resize, luma, multi-scale Sobel,
+local variance, exact-order-statistic quantiles, smoothing, shaping -- all on the device, no
+host round trip); a CPU target takes the plain torch ops below, which follow the reference
+one to one and double as the fp32 reference of the CUDA path in the tests."""
 from __future__ import annotations
 
 import torch
@@ -61,6 +64,11 @@ def compute_importance_mask(
     """[H0,W0,3] target -> [H,W] weights in [floor', 1]: multi-scale Sobel energy and 9x9
     local variance, each robustly normalised, mixed, optionally box-smoothed, gamma-shaped,
     lifted to `floor` and blended towards 1 by (1 - strength)."""
+    if target_hw3.is_cuda:
+        from ggs_b200 import importance_mask
+        return importance_mask(target_hw3, H, W, edge_scales=edge_scales, w_edge=w_edge,
+                               w_var=w_var, gamma=gamma, floor=floor, smooth=smooth,
+                               strength=strength)
     x = _unit_range(target_hw3).permute(2, 0, 1)[None]
     x = F.interpolate(x, size=(H, W), mode='bilinear', align_corners=False)
     y = _rgb_to_luma(x[0].permute(1, 2, 0))

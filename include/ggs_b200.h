@@ -163,6 +163,27 @@ int ggs_ga_breed(const float *d_population, const float *d_fitness, int P, int N
                  float log_scale_lo, float log_scale_hi, uint64_t seed, uint32_t generation,
                  void *stream);
 
+/* ---- importance mask, the weight_mask input of the fitness ---- */
+
+/*
+ * compute_importance_mask (modules/mask.py:29-83) on the device: bilinear resize of the source
+ * image to the work size (mask.py:47), Rec.709 luma (mask.py:6-10), multi-scale Sobel energy
+ * (mask.py:50-59), 9x9 local variance (mask.py:21-25, 62), the 2nd..98th percentile
+ * normalisation with torch.quantile's linear interpolation (mask.py:65-69), mix (mask.py:73),
+ * optional box smoothing (mask.py:75-77), gamma / floor / strength (mask.py:79-86).
+ * d_image: [H0][W0][3]; image_is_0_255 != 0 divides by 255 first (the reference decides this
+ * with `x.max() > 1.5`, mask.py:45; the caller makes that test).  h_edge_scales: n_scales
+ * integers >= 1, each <= min(H, W).  smooth: 0 (off) or an odd box size.  The scalar
+ * parameters are doubles because the reference does its scalar arithmetic (1.0 - floor,
+ * 1.0 - strength) in Python floats before rounding to float32.
+ * d_mask: [H][W].  Workspace: ggs_mask_workspace_bytes(H, W), caller-owned like the others.
+ */
+size_t ggs_mask_workspace_bytes(int H, int W);
+int ggs_importance_mask(const float *d_image, int H0, int W0, int H, int W, int image_is_0_255,
+                        const int *h_edge_scales, int n_scales, double w_edge, double w_var,
+                        double gamma, double floor, int smooth, double strength, float *d_mask,
+                        void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* ---- hardware probes used by bench.py for the roofline denominators -------------- */
 
 /*
