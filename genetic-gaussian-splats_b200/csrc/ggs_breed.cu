@@ -9,6 +9,21 @@
 // which it runs per individual in Python (about 40 launches and 4-6 .item() syncs each).
 // Here one CTA breeds one offspring pair; the population tensor never leaves the device.
 //
+// The job is to read two parents and write two children (36 B per splat each): HBM-bound if the
+// arithmetic stays out of the way.  Three things keep it there:
+//  * rows move through shared memory 256 at a time with element-wise, fully coalesced loads and
+//    stores (a 9-float row per thread would touch every 128-byte line nine times) and are worked
+//    on in place there (row stride 9 floats: conflict-free);
+//  * randomness is spent only where it is used: one Philox call per (child, splat) yields the
+//    seven Bernoulli flags (16-bit uniforms) and the crossover coin, and Gaussian noise is drawn
+//    per (row, gene group) *item* -- the mutated groups of a chunk are compacted into a list and
+//    processed densely, so a mutation rate of 10 % costs 10 % of the Box-Muller work instead
+//    of a divergent branch that nearly every warp takes;
+//  * the size-ordered swap scans the children while they are still in shared memory instead of
+//    reading them back.
+// Genomes with extra columns (cols > 9) or too many splats for the mask cache take a direct
+// path (thread per row, global memory); both paths use the same counters and produce the same bits.
+//
 // Randomness is counter based (Philox4x32-10 keyed by the seed, counters = generation, child,
 // splat, stream), so a step is reproducible for a given (seed, generation) and independent of
 // the launch geometry.  The operators draw from the same distributions as the reference; the
@@ -21,6 +36,8 @@ namespace ggs {
 namespace {
 
 constexpr int kBreedThreads = 256;
+constexpr int kGroups = 5;  // xy, log-scales, theta, rgb, alpha
+constexpr size_t kStageBytes = (size_t)2 * 2 * kBreedThreads * 9 * sizeof(float);
 
 struct U4 {
     unsigned x, y, z, w;
@@ -44,20 +61,37 @@ __device__ __forceinline__ U4 philox4x32_10(unsigned c0, unsigned c1, unsigned c
     return {c0, c1, c2, c3};
 }
 
+// 4-byte asynchronous global -> shared copy (LDGSTS): the next chunk of parent rows streams in
+// while the current one is being worked on.
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ float u01(unsigned v) { return (float)(v >> 8) * (1.0f / 16777216.0f); }
 
 // Two standard normals from two 32-bit words (Box-Muller).
 __device__ __forceinline__ float2 normal2(unsigned a, unsigned b)
 {
+    // Hardware approximations (lg2 / sin / cos, absolute error ~2^-21): mutation noise needs the
+    // right distribution, not last-bit accuracy, and the full-accuracy library calls were the
+    // largest single item of the kernel's instruction count.
     const float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);  // (0, 1]
-    const float r = sqrtf(-2.0f * logf(u1));
+    const float r = sqrtf(-2.0f * __logf(u1));
     float s, c;
-    sincospif(2.0f * u01(b), &s, &c);
+    __sincosf(6.28318530717958647692f * (u01(b) - 0.5f), &s, &c);     // angle in [-pi, pi)
     return make_float2(r * c, r * s);
 }
 
-enum Stream : unsigned { kSelect = 1, kCross = 2, kMask = 3, kNoise0 = 4, kNoise1 = 5, kNoise2 = 6,
-                         kForce = 7, kSwapIdx = 8, kSwapScore = 9 };
+enum Stream : unsigned { kSelect = 1, kCross = 2, kMask = 3, kNoise = 4 /* +group */,
+                         kForce = 16, kSwapIdx = 17, kSwapScore = 18 };
 
 struct BreedParams {
     const float *pop;
@@ -65,49 +99,127 @@ struct BreedParams {
     float *off;
     int P, N, cols;
     int tour_k;
-    float cxpb, mutpb;
+    float cxpb;
+    unsigned mut_thr;  // mutpb as a 16-bit threshold: flag = (16-bit uniform < mut_thr)
     float s_xy, s_alog, s_blog, s_theta, s_rgb, s_alpha;
     float log_lo, log_hi;
     unsigned seed_lo, seed_hi, gen;
 };
 
-// Bernoulli(mutpb) masks of one splat: bit0,1 = x,y  bit2,3 = log sx, log sy  bit4 = theta
-// bit5 = rgb flag  bit6 = alpha flag   (genetic.py:42-50)
+// One Philox call per (child, splat): seven Bernoulli(mutpb) flags from 16-bit uniforms
+//   bit0,1 = x,y   bit2,3 = log sx, log sy   bit4 = theta   bit5 = rgb flag   bit6 = alpha flag
+// (genetic.py:42-50) and, in bit 7, a fair coin: the row's crossover side (genetic.py:18), which
+// is read from the pair's first child.
+constexpr unsigned kFlagBits = 0x7fu, kCoinBit = 0x80u;
 __device__ __forceinline__ unsigned gene_masks(const BreedParams &q, unsigned child, unsigned n)
 {
     const U4 a = philox4x32_10(q.gen, child, n, kMask, q.seed_lo, q.seed_hi);
-    const U4 b = philox4x32_10(q.gen, child, n, kMask + 64u, q.seed_lo, q.seed_hi);
     unsigned m = 0;
-    m |= (u01(a.x) < q.mutpb) ? 1u : 0u;
-    m |= (u01(a.y) < q.mutpb) ? 2u : 0u;
-    m |= (u01(a.z) < q.mutpb) ? 4u : 0u;
-    m |= (u01(a.w) < q.mutpb) ? 8u : 0u;
-    m |= (u01(b.x) < q.mutpb) ? 16u : 0u;
-    m |= (u01(b.y) < q.mutpb) ? 32u : 0u;
-    m |= (u01(b.z) < q.mutpb) ? 64u : 0u;
+    m |= ((a.x & 0xffffu) < q.mut_thr) ? 1u : 0u;
+    m |= ((a.x >> 16) < q.mut_thr) ? 2u : 0u;
+    m |= ((a.y & 0xffffu) < q.mut_thr) ? 4u : 0u;
+    m |= ((a.y >> 16) < q.mut_thr) ? 8u : 0u;
+    m |= ((a.z & 0xffffu) < q.mut_thr) ? 16u : 0u;
+    m |= ((a.z >> 16) < q.mut_thr) ? 32u : 0u;
+    m |= ((a.w & 0xffffu) < q.mut_thr) ? 64u : 0u;
+    m |= ((a.w >> 16) & 1u) ? kCoinBit : 0u;
     return m;
+}
+
+// Which gene groups of a row mutate: bit g set iff any flag of group g is set.
+__device__ __forceinline__ unsigned group_bits(unsigned m)
+{
+    return ((m & 3u) ? 1u : 0u) | ((m & 12u) ? 2u : 0u) | ((m & 16u) ? 4u : 0u) |
+           ((m & 32u) ? 8u : 0u) | ((m & 64u) ? 16u : 0u);
+}
+
+// Gaussian mutation of gene group `grp` of one row (genetic.py:61-72); `row` is 9 floats in any
+// address space.  The noise is a pure function of (generation, child, splat, group).
+template <typename Row>
+__device__ __forceinline__ void mutate_group(const BreedParams &q, unsigned child, unsigned n,
+                                             int grp, unsigned m, Row &&row)
+{
+    const U4 r = philox4x32_10(q.gen, child, n, kNoise + (unsigned)grp, q.seed_lo, q.seed_hi);
+    const float2 z = normal2(r.x, r.y);
+    if (grp == 0) {
+        if (m & 1u) row[0] += z.x * q.s_xy;
+        if (m & 2u) row[1] += z.y * q.s_xy;
+    } else if (grp == 1) {
+        if (m & 4u) row[2] += z.x * q.s_alog;
+        if (m & 8u) row[3] += z.y * q.s_blog;
+    } else if (grp == 2) {
+        row[4] += z.x * q.s_theta;
+    } else if (grp == 3) {  // one flag for the three colour channels, independent noise
+        const float2 z2 = normal2(r.z, r.w);
+        row[5] += z.x * q.s_rgb;
+        row[6] += z.y * q.s_rgb;
+        row[7] += z2.x * q.s_rgb;
+    } else {
+        row[8] += z.x * q.s_alpha;
+    }
 }
 
 __device__ __forceinline__ float wrap_angle(float t)
 {
+    // (t + pi) mod 2pi - pi (genetic.py:66): floor form; an angle already in range passes
+    // through floor(...) = 0 exactly as it does through fmod.
     const float kPi = 3.14159265358979323846f, k2Pi = 6.28318530717958647692f;
-    float v = fmodf(t + kPi, k2Pi);
+    float v = t + kPi;
+    v -= k2Pi * floorf(v * (1.0f / k2Pi));
     if (v < 0.0f) v += k2Pi;
+    if (v >= k2Pi) v -= k2Pi;
     return v - kPi;
 }
 
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
 
+// Projection onto the legal box (utils.py:36-45).
+__device__ __forceinline__ void project_row(const BreedParams &q, float (&g)[9])
+{
+    g[0] = clampf(g[0], 0.0f, 1.0f);
+    g[1] = clampf(g[1], 0.0f, 1.0f);
+    g[2] = clampf(g[2], q.log_lo, q.log_hi);
+    g[3] = clampf(g[3], q.log_lo, q.log_hi);
+    g[4] = wrap_angle(g[4]);
+#pragma unroll
+    for (int k = 5; k < 9; ++k) g[k] = clampf(g[k], 0.0f, 255.0f);
+}
+
+// Swap candidate j of a child (a later, bigger splat): uniform choice = arg max of iid scores.
+// The score is a 32-bit integer hash (murmur3 finaliser) of j under a per-child Philox salt: a
+// full Philox call per candidate cost more than everything else done to the row.
+__device__ __forceinline__ unsigned long long swap_key(unsigned salt, int j)
+{
+    unsigned h = (unsigned)j * 0x9E3779B9u + salt;
+    h ^= h >> 16;
+    h *= 0x85EBCA6Bu;
+    h ^= h >> 13;
+    h *= 0xC2B2AE35u;
+    h ^= h >> 16;
+    return ((unsigned long long)(h | 1u) << 32) | (unsigned)j;
+}
+
+// kStaged: cols == 9 and the mask cache fits; dynamic shared memory =
+//   2 buffers x 2 parents x (kBreedThreads x 9) floats of row staging + 2 x N bytes of masks.
+template <bool kStaged>
 __global__ void __launch_bounds__(kBreedThreads) breed_kernel(BreedParams q)
 {
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    float *s_stage = reinterpret_cast<float *>(s_dyn);   // [buffer][parent / child][row][9]
+    unsigned char *s_mask = s_dyn + kStageBytes;           // [2][N]
+    __shared__ unsigned short s_items[2 * kBreedThreads * kGroups];  // child << 11 | row << 3 | group
+    __shared__ unsigned char s_cmask[2][kBreedThreads];              // the chunk's masks, forced bits in
+    __shared__ int s_nitems;
     __shared__ int s_parent[2];
     __shared__ int s_docx;
     __shared__ int s_count[2][4];   // mutated genes per child and group (xy, ab, theta, colour)
     __shared__ int s_force[2][4];   // forced element when a group came out empty, else -1
     __shared__ unsigned long long s_best[2];
     __shared__ int s_swap_i[2];
+    __shared__ unsigned s_swap_salt[2];
+    __shared__ float s_size_i[2];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int pair = blockIdx.x;
     const int nchild = (2 * pair + 1 < q.P) ? 2 : 1;
 
@@ -135,15 +247,48 @@ __global__ void __launch_bounds__(kBreedThreads) breed_kernel(BreedParams q)
         (&s_count[0][0])[tid] = 0;
         (&s_force[0][0])[tid] = -1;
     }
-    if (tid < 2) s_best[tid] = 0ull;
+    if (tid < 2) {
+        s_best[tid] = 0ull;
+        // the splat that may be swapped back: uniform in [0, N-2] (genetic.py:76)
+        const U4 r = philox4x32_10(q.gen, 2 * pair + tid, 0, kSwapIdx, q.seed_lo, q.seed_hi);
+        s_swap_i[tid] = (q.N >= 2) ? (int)__umulhi(r.x, (unsigned)(q.N - 1)) : 0;
+        s_swap_salt[tid] = r.y;
+    }
     __syncthreads();
 
-    // ---- pass 1: how many genes of each group mutate (for the "at least one" rule)
+    const float *pa = q.pop + (int64_t)s_parent[0] * q.N * q.cols;
+    const float *pb = q.pop + (int64_t)s_parent[1] * q.N * q.cols;
+    // Stream chunk `n0` of both parents into staging buffer `buf`: element-wise, so a warp
+    // moves 128 contiguous bytes per instruction whatever the row alignment.
+    // 16-byte copies when every row block starts on a 16-byte boundary (N a multiple of 4 and
+    // aligned tensors; a chunk is 256 rows = 9,216 B): a quarter of the copy instructions.
+    const bool vec = ((q.N & 3) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(q.pop) | reinterpret_cast<uintptr_t>(q.off)) & 15u) == 0;
+    auto prefetch = [&](int n0, int buf) {
+        const int nfl = min(kBreedThreads, q.N - n0) * 9;
+        float *dst = s_stage + buf * (2 * kBreedThreads * 9);
+        const float *ga = pa + (int64_t)n0 * 9, *gb = pb + (int64_t)n0 * 9;
+        if (vec) {  // nfl is a multiple of 4 as well (rows is: N and the chunk size are)
+            for (int i = 4 * tid; i < nfl; i += 4 * kBreedThreads) {
+                cp_async16(dst + i, ga + i);
+                cp_async16(dst + kBreedThreads * 9 + i, gb + i);
+            }
+        } else {
+            for (int i = tid; i < nfl; i += kBreedThreads) {
+                cp_async4(dst + i, ga + i);
+                cp_async4(dst + kBreedThreads * 9 + i, gb + i);
+            }
+        }
+    };
+    if (kStaged) prefetch(0, 0);  // lands while the masks are drawn
+
+    // ---- pass 1: draw the masks; how many genes of each group mutate ("at least one" rule)
     for (int c = 0; c < nchild; ++c) {
         const unsigned child = 2 * pair + c;
         int cnt[4] = {0, 0, 0, 0};
         for (int n = tid; n < q.N; n += kBreedThreads) {
             const unsigned m = gene_masks(q, child, n);
+            if (kStaged) s_mask[c * q.N + n] = (unsigned char)m;
             cnt[0] += __popc(m & 3u);
             cnt[1] += __popc(m & 12u);
             cnt[2] += __popc(m & 16u);
@@ -154,7 +299,7 @@ __global__ void __launch_bounds__(kBreedThreads) breed_kernel(BreedParams q)
             int v = cnt[g];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((tid & 31) == 0 && v) atomicAdd(&s_count[c][g], v);
+            if (lane == 0 && v) atomicAdd(&s_count[c][g], v);
         }
     }
     __syncthreads();
@@ -169,98 +314,171 @@ __global__ void __launch_bounds__(kBreedThreads) breed_kernel(BreedParams q)
     }
     __syncthreads();
 
-    // ---- pass 2: crossover, mutation, projection; one thread per splat
-    const float *pa = q.pop + (int64_t)s_parent[0] * q.N * q.cols;
-    const float *pb = q.pop + (int64_t)s_parent[1] * q.N * q.cols;
-    for (int n = tid; n < q.N; n += kBreedThreads) {
-        bool take_a = true;
-        if (s_docx) {
-            const U4 r = philox4x32_10(q.gen, pair, n, kCross + 64u, q.seed_lo, q.seed_hi);
-            take_a = (r.x & 1u) != 0u;  // p = 0.5 per row (genetic.py:18)
-        }
-        for (int c = 0; c < nchild; ++c) {
-            const unsigned child = 2 * pair + c;
-            const float *src = ((c == 0) == take_a ? pa : pb) + (int64_t)n * q.cols;
-            float g[9];
+    // ---- pass 2: crossover, mutation, projection
+    const int f[2][4] = {{s_force[0][0], s_force[0][1], s_force[0][2], s_force[0][3]},
+                         {s_force[1][0], s_force[1][1], s_force[1][2], s_force[1][3]}};
+    auto forced = [&](int c, int n, unsigned m) {
+        m &= kFlagBits;
+        if (f[c][0] >= 0 && (f[c][0] >> 1) == n) m |= 1u << (f[c][0] & 1);
+        if (f[c][1] >= 0 && (f[c][1] >> 1) == n) m |= 4u << (f[c][1] & 1);
+        if (f[c][2] >= 0 && f[c][2] == n) m |= 16u;
+        if (f[c][3] >= 0 && (f[c][3] >> 1) == n) m |= 32u << (f[c][3] & 1);
+        return m;
+    };
+    const int swap_i[2] = {s_swap_i[0], s_swap_i[1]};
+    const unsigned swap_salt[2] = {s_swap_salt[0], s_swap_salt[1]};
+    unsigned long long best[2] = {0ull, 0ull};  // this thread's best swap candidate per child
+
+    if (kStaged) {
+        float *off[2] = {q.off + (int64_t)(2 * pair) * q.N * 9, q.off + (int64_t)(2 * pair + 1) * q.N * 9};
+        for (int n0 = 0, buf = 0; n0 < q.N; n0 += kBreedThreads, buf ^= 1) {
+            const int rows = min(kBreedThreads, q.N - n0), nfl = rows * 9;
+            float *s_rows[2] = {s_stage + buf * (2 * kBreedThreads * 9),
+                                s_stage + buf * (2 * kBreedThreads * 9) + kBreedThreads * 9};
+            if (tid == 0) s_nitems = 0;
+            cp_async_wait_all();
+            __syncthreads();  // this chunk has landed; the other buffer was stored and is free
+            if (n0 + kBreedThreads < q.N) prefetch(n0 + kBreedThreads, buf ^ 1);
+
+            // (a) crossover side of the row, masks, list of (row, group) items that need noise
+            unsigned gm[2] = {0u, 0u};
+            if (tid < rows) {
+                const int n = n0 + tid;
+                const unsigned m0 = s_mask[n];
+                if (s_docx && !(m0 & kCoinBit)) {  // child 0 takes this row from parent b
 #pragma unroll
-            for (int k = 0; k < 9; ++k) g[k] = __ldg(src + k);
-
-            unsigned m = gene_masks(q, child, n);
-            const int f0 = s_force[c][0], f1 = s_force[c][1], f2 = s_force[c][2], f3 = s_force[c][3];
-            if (f0 >= 0 && (f0 >> 1) == n) m |= 1u << (f0 & 1);
-            if (f1 >= 0 && (f1 >> 1) == n) m |= 4u << (f1 & 1);
-            if (f2 >= 0 && f2 == n) m |= 16u;
-            if (f3 >= 0 && (f3 >> 1) == n) m |= 32u << (f3 & 1);
-
-            if (m) {
-                const U4 r0 = philox4x32_10(q.gen, child, n, kNoise0, q.seed_lo, q.seed_hi);
-                const U4 r1 = philox4x32_10(q.gen, child, n, kNoise1, q.seed_lo, q.seed_hi);
-                const U4 r2 = philox4x32_10(q.gen, child, n, kNoise2, q.seed_lo, q.seed_hi);
-                const float2 z01 = normal2(r0.x, r0.y), z23 = normal2(r0.z, r0.w);
-                const float2 z45 = normal2(r1.x, r1.y), z67 = normal2(r1.z, r1.w);
-                const float2 z89 = normal2(r2.x, r2.y);
-                if (m & 1u) g[0] += z01.x * q.s_xy;
-                if (m & 2u) g[1] += z01.y * q.s_xy;
-                if (m & 4u) g[2] += z23.x * q.s_alog;
-                if (m & 8u) g[3] += z23.y * q.s_blog;
-                if (m & 16u) g[4] += z45.x * q.s_theta;
-                if (m & 32u) {  // one flag for the three colour channels, independent noise
-                    g[5] += z45.y * q.s_rgb;
-                    g[6] += z67.x * q.s_rgb;
-                    g[7] += z67.y * q.s_rgb;
+                    for (int k = 0; k < 9; ++k) {
+                        const float va = s_rows[0][tid * 9 + k];
+                        s_rows[0][tid * 9 + k] = s_rows[1][tid * 9 + k];
+                        s_rows[1][tid * 9 + k] = va;
+                    }
                 }
-                if (m & 64u) g[8] += z89.x * q.s_alpha;
+                for (int c = 0; c < nchild; ++c) {
+                    const unsigned m = forced(c, n, c ? s_mask[q.N + n] : m0);
+                    s_cmask[c][tid] = (unsigned char)m;
+                    gm[c] = group_bits(m);
+                }
             }
-            // projection onto the legal box (utils.py:36-45)
-            g[0] = clampf(g[0], 0.0f, 1.0f);
-            g[1] = clampf(g[1], 0.0f, 1.0f);
-            g[2] = clampf(g[2], q.log_lo, q.log_hi);
-            g[3] = clampf(g[3], q.log_lo, q.log_hi);
-            g[4] = wrap_angle(g[4]);
+            const int mine = __popc(gm[0]) + __popc(gm[1]);
+            int incl = mine;
 #pragma unroll
-            for (int k = 5; k < 9; ++k) g[k] = clampf(g[k], 0.0f, 255.0f);
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int base = 0;
+            if (lane == 31 && incl) base = atomicAdd(&s_nitems, incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            int pos = base + incl - mine;
+            for (int c = 0; c < 2; ++c)
+                for (unsigned g = gm[c]; g; g &= g - 1u)
+                    s_items[pos++] = (unsigned short)((c << 11) | (tid << 3) | (__ffs(g) - 1));
+            __syncthreads();
 
-            float *dst = q.off + ((int64_t)child * q.N + n) * 9;
+            // (b) the noise, one item per thread
+            for (int i = tid; i < s_nitems; i += kBreedThreads) {
+                const unsigned it = s_items[i];
+                const int c = it >> 11, t = (it >> 3) & 255, grp = it & 7;
+                mutate_group(q, 2 * pair + c, n0 + t, grp, s_cmask[c][t], s_rows[c] + t * 9);
+            }
+            __syncthreads();
+
+            // (c) projection, in place; the reference row of the swap announces its size
+            if (tid < rows) {
+                for (int c = 0; c < nchild; ++c) {
+                    float g[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) dst[k] = g[k];
+                    for (int k = 0; k < 9; ++k) g[k] = s_rows[c][tid * 9 + k];
+                    project_row(q, g);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) s_rows[c][tid * 9 + k] = g[k];
+                    if (n0 + tid == swap_i[c]) s_size_i[c] = g[2] + g[3];  // log(sigma_x * sigma_y)
+                }
+            }
+            __syncthreads();
+
+            // (d) later, bigger splats are swap candidates (genetic.py:77-83); store the chunk
+            if (tid < rows && q.N >= 2) {
+                for (int c = 0; c < nchild; ++c) {
+                    const int j = n0 + tid;
+                    if (j > swap_i[c] &&
+                        s_rows[c][tid * 9 + 2] + s_rows[c][tid * 9 + 3] > s_size_i[c]) {
+                        const unsigned long long key = swap_key(swap_salt[c], j);
+                        best[c] = key > best[c] ? key : best[c];
+                    }
+                }
+            }
+            if (vec) {
+                for (int i = 4 * tid; i < nfl; i += 4 * kBreedThreads) {
+                    *reinterpret_cast<float4 *>(off[0] + (int64_t)n0 * 9 + i) =
+                        *reinterpret_cast<const float4 *>(s_rows[0] + i);
+                    if (nchild == 2)
+                        *reinterpret_cast<float4 *>(off[1] + (int64_t)n0 * 9 + i) =
+                            *reinterpret_cast<const float4 *>(s_rows[1] + i);
+                }
+            } else {
+                for (int i = tid; i < nfl; i += kBreedThreads) {
+                    off[0][(int64_t)n0 * 9 + i] = s_rows[0][i];
+                    if (nchild == 2) off[1][(int64_t)n0 * 9 + i] = s_rows[1][i];
+                }
+            }
+            __syncthreads();
+        }
+    } else {
+        for (int n = tid; n < q.N; n += kBreedThreads) {
+            const unsigned m0 = gene_masks(q, 2 * pair, n);
+            const bool take_a = !s_docx || (m0 & kCoinBit);
+            for (int c = 0; c < nchild; ++c) {
+                const unsigned child = 2 * pair + c;
+                const float *src = ((c == 0) == take_a ? pa : pb) + (int64_t)n * q.cols;
+                float g[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) g[k] = __ldg(src + k);
+                const unsigned m = forced(c, n, c ? gene_masks(q, child, n) : m0);
+                const unsigned gmask = group_bits(m);
+#pragma unroll
+                for (int grp = 0; grp < kGroups; ++grp)
+                    if (gmask & (1u << grp)) mutate_group(q, child, n, grp, m, g);
+                project_row(q, g);
+                float *dst = q.off + ((int64_t)child * q.N + n) * 9;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) dst[k] = g[k];
+            }
+        }
+        __syncthreads();  // the child rows written above are read back below by other threads
+        // bring a bigger later splat forward (genetic.py:74-91): candidates from global memory
+        if (q.N >= 2) {
+            for (int c = 0; c < nchild; ++c) {
+                const float *row = q.off + (int64_t)(2 * pair + c) * q.N * 9;
+                const int i = swap_i[c];
+                const float size_i = row[i * 9 + 2] + row[i * 9 + 3];
+                for (int j = i + 1 + tid; j < q.N; j += kBreedThreads) {
+                    if (row[j * 9 + 2] + row[j * 9 + 3] > size_i) {
+                        const unsigned long long key = swap_key(swap_salt[c], j);
+                        best[c] = key > best[c] ? key : best[c];
+                    }
+                }
+            }
         }
     }
-    __syncthreads();  // the child rows written above are read back below by other threads
 
-    // ---- pass 3: bring a bigger later splat forward (genetic.py:74-91)
+    // ---- pass 3: the swap itself
     if (q.N >= 2) {
-        if (tid < nchild) {
-            const U4 r = philox4x32_10(q.gen, 2 * pair + tid, 0, kSwapIdx, q.seed_lo, q.seed_hi);
-            s_swap_i[tid] = (int)__umulhi(r.x, (unsigned)(q.N - 1));  // uniform in [0, N-2]
-        }
-        __syncthreads();
         for (int c = 0; c < nchild; ++c) {
-            const unsigned child = 2 * pair + c;
-            const float *row = q.off + (int64_t)child * q.N * 9;
-            const int i = s_swap_i[c];
-            const float size_i = row[i * 9 + 2] + row[i * 9 + 3];  // log(sigma_x * sigma_y)
-            unsigned long long best = 0ull;
-            for (int j = i + 1 + tid; j < q.N; j += kBreedThreads) {
-                if (row[j * 9 + 2] + row[j * 9 + 3] > size_i) {
-                    // uniform choice among the candidates = arg max of iid scores
-                    const U4 r = philox4x32_10(q.gen, child, j, kSwapScore, q.seed_lo, q.seed_hi);
-                    const unsigned long long key = ((unsigned long long)(r.x | 1u) << 32) | (unsigned)j;
-                    best = key > best ? key : best;
-                }
-            }
+            unsigned long long b = best[c];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-                best = other > best ? other : best;
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, b, o);
+                b = other > b ? other : b;
             }
-            if ((tid & 31) == 0 && best) atomicMax(&s_best[c], best);
+            if (lane == 0 && b) atomicMax(&s_best[c], b);
         }
-        __syncthreads();
+        __syncthreads();  // also orders the chunk stores above before the row exchange below
         if (tid < 9 * nchild) {
             const int c = tid / 9, k = tid - 9 * c;
             if (s_best[c] != 0ull) {
                 float *row = q.off + (int64_t)(2 * pair + c) * q.N * 9;
-                const int i = s_swap_i[c], j = (int)(s_best[c] & 0xffffffffull);
+                const int i = swap_i[c], j = (int)(s_best[c] & 0xffffffffull);
                 const float a = row[i * 9 + k], b = row[j * 9 + k];
                 row[i * 9 + k] = b;
                 row[j * 9 + k] = a;
@@ -286,7 +504,8 @@ cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int 
     q.cols = cols;
     q.tour_k = tour_k;
     q.cxpb = cxpb;
-    q.mutpb = mutpb;
+    const float thr = rintf(fminf(fmaxf(mutpb, 0.0f), 1.0f) * 65536.0f);
+    q.mut_thr = (unsigned)thr;  // 0 .. 65536: Bernoulli(mutpb) to 1.5e-5
     q.s_xy = sigma6[0];
     q.s_alog = sigma6[1];
     q.s_blog = sigma6[2];
@@ -298,7 +517,18 @@ cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int 
     q.seed_lo = (unsigned)(seed & 0xffffffffu);
     q.seed_hi = (unsigned)(seed >> 32);
     q.gen = generation;
-    breed_kernel<<<(P + 1) / 2, kBreedThreads, 0, stream>>>(q);
+    const size_t staged_bytes = kStageBytes + (size_t)2 * N;
+    if (cols == 9 && staged_bytes <= (size_t)200 * 1024) {
+        if (staged_bytes > (size_t)36 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(breed_kernel<true>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)staged_bytes);
+            if (e != cudaSuccess) return e;
+        }
+        breed_kernel<true><<<(P + 1) / 2, kBreedThreads, staged_bytes, stream>>>(q);
+    } else {
+        breed_kernel<false><<<(P + 1) / 2, kBreedThreads, 0, stream>>>(q);
+    }
     return cudaGetLastError();
 }
 

@@ -184,3 +184,28 @@ def test_ga_loop_uses_the_kernel_and_improves(ggs):
     torch.manual_seed(0)
     _, f2 = genetic_approx(target, H, W, "cuda", generations=80, **kw)
     assert f1 < 0.9 * f0 and f1 == f2              # improves, and reproducible for a fixed seed
+
+
+@pytest.mark.parametrize("P,N", [(7, 1), (6, 255), (5, 256), (4, 257), (3, 1000), (2, 4000)])
+def test_staged_and_direct_paths_are_bit_identical(ggs, P, N):
+    """9-column genomes go through the shared-memory staging and the cached masks; the same
+    genomes with two extra columns take the direct path.  Same counters, same bits."""
+    pop = population(P, N, seed=P)
+    fit = torch.rand(P, device="cuda")
+    padded = torch.cat([pop, torch.full((P, N, 2), 123.0, device="cuda")], dim=-1).contiguous()
+    for kw in (dict(cxpb=0.9, mutpb=0.2), dict(cxpb=0.0, mutpb=0.0), dict(cxpb=1.0, mutpb=1.0)):
+        a = breed(ggs, pop, fit, **kw)
+        b = breed(ggs, padded, fit, **kw)
+        assert a.shape == b.shape == (P, N, 9)
+        assert torch.equal(a, b), (P, N, kw)
+
+
+def test_large_splat_count_uses_the_direct_path(ggs):
+    # beyond the mask cache (2 bytes per splat in shared memory): still correct and reproducible
+    P, N = 2, 120_000
+    pop = population(P, N, seed=3)
+    fit = torch.rand(P, device="cuda")
+    a = breed(ggs, pop, fit, mutpb=0.01)
+    assert torch.isfinite(a).all() and torch.equal(a, breed(ggs, pop, fit, mutpb=0.01))
+    changed = (a != pop[0]).any(dim=-1).float().mean() + (a != pop[1]).any(dim=-1).float().mean()
+    assert changed > 0
