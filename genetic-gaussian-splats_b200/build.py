@@ -31,6 +31,7 @@ SOURCES = {
     "ggs_raster.cu": [],
     "ggs_breed.cu": [],
     "ggs_mask.cu": ["-fmad=false"],   # one rounding per operation, like the reference's torch ops
+    "ggs_engine.cu": [],
     "ggs_probe.cu": [],
     "ggs_api.cu": [],
 }

@@ -110,7 +110,7 @@ static cudaEvent_t *timing_slot()
 }
 
 // decode + raster on `stream`; the one launch sequence behind every public entry.
-static int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
+int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
                     float k_sigma, const float bg[3], const float *d_target, const float *d_mask,
                     int mode, float beta, float *d_fitness, void *d_images, int image_u8,
                     void *d_workspace, size_t workspace_bytes_given, cudaStream_t stream)
@@ -458,7 +458,7 @@ int ggs_ga_breed(const float *d_population, const float *d_fitness, int P, int N
         set_error("ggs_ga_breed: offspring must not alias the population");
         return GGS_EINVAL;
     }
-    GGS_CUDA(launch_breed(d_population, d_fitness, P, N, cols, d_offspring, tour_k, cxpb, mutpb,
+    GGS_CUDA(launch_breed(d_population, d_fitness, P, N, cols, P, d_offspring, tour_k, cxpb, mutpb,
                           h_sigma6, log_scale_lo, log_scale_hi, seed, generation,
                           static_cast<cudaStream_t>(stream)));
     return GGS_OK;

@@ -98,6 +98,7 @@ struct BreedParams {
     const float *fitness;
     float *off;
     int P, N, cols;
+    int n_children;  // children to produce: the first n_children of the P the step defines
     int tour_k;
     float cxpb;
     unsigned mut_thr;  // mutpb as a 16-bit threshold: flag = (16-bit uniform < mut_thr)
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kBreedThreads) breed_kernel(BreedParams q)
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int pair = blockIdx.x;
-    const int nchild = (2 * pair + 1 < q.P) ? 2 : 1;
+    const int nchild = (2 * pair + 1 < q.n_children) ? 2 : 1;
 
     if (tid == 0) {
         // two independent tournaments: a shuffled list of iid tournament winners paired up
@@ -490,11 +491,11 @@ __global__ void __launch_bounds__(kBreedThreads) breed_kernel(BreedParams q)
 }  // namespace
 
 cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int N, int cols,
-                         float *d_offspring, int tour_k, float cxpb, float mutpb,
+                         int n_children, float *d_offspring, int tour_k, float cxpb, float mutpb,
                          const float sigma6[6], float log_lo, float log_hi, uint64_t seed,
                          uint32_t generation, cudaStream_t stream)
 {
-    if (P <= 0 || N <= 0) return cudaSuccess;
+    if (P <= 0 || N <= 0 || n_children <= 0) return cudaSuccess;
     BreedParams q;
     q.pop = d_pop;
     q.fitness = d_fitness;
@@ -502,6 +503,7 @@ cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int 
     q.P = P;
     q.N = N;
     q.cols = cols;
+    q.n_children = n_children < P ? n_children : P;
     q.tour_k = tour_k;
     q.cxpb = cxpb;
     const float thr = rintf(fminf(fmaxf(mutpb, 0.0f), 1.0f) * 65536.0f);
@@ -525,9 +527,9 @@ cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int 
                                                  (int)staged_bytes);
             if (e != cudaSuccess) return e;
         }
-        breed_kernel<true><<<(P + 1) / 2, kBreedThreads, staged_bytes, stream>>>(q);
+        breed_kernel<true><<<(q.n_children + 1) / 2, kBreedThreads, staged_bytes, stream>>>(q);
     } else {
-        breed_kernel<false><<<(P + 1) / 2, kBreedThreads, 0, stream>>>(q);
+        breed_kernel<false><<<(q.n_children + 1) / 2, kBreedThreads, 0, stream>>>(q);
     }
     return cudaGetLastError();
 }

@@ -72,8 +72,10 @@ cudaError_t launch_raster(const Workspace &ws, int B, int N, int H, int W, const
                           unsigned long long *d_stats, cudaStream_t stream);
 
 // breed.cu
+// The step defines P children; only the first n_children are produced (counter-based streams:
+// child c is the same whatever n_children is).
 cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int N, int cols,
-                         float *d_offspring, int tour_k, float cxpb, float mutpb,
+                         int n_children, float *d_offspring, int tour_k, float cxpb, float mutpb,
                          const float sigma6[6], float log_lo, float log_hi, uint64_t seed,
                          uint32_t generation, cudaStream_t stream);
 
@@ -88,5 +90,11 @@ cudaError_t launch_importance_mask(const float *d_image, int H0, int W0, int H, 
 cudaError_t probe_peaks(float *h_out5);
 
 void set_error(const char *fmt, ...);
+
+// api.cu: decode + raster on `stream`, the launch sequence behind every evaluation entry.
+int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
+             float k_sigma, const float bg[3], const float *d_target, const float *d_mask,
+             int mode, float beta, float *d_fitness, void *d_images, int image_u8,
+             void *d_workspace, size_t workspace_bytes_given, cudaStream_t stream);
 
 }  // namespace ggs

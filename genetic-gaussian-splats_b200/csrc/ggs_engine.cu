@@ -1,0 +1,407 @@
+// GA generations without the host in the loop (SURVEY.md section 8f "next" #1: the batched
+// on-device GA step *including elitism*, algorithm.py:87-160).
+//
+// The reference's default run is 500,000 generations of a 32-individual population
+// (modules/config.py): each generation is tens of microseconds of GPU work, so what decides the
+// run time is whether the host has to look at the fitness vector in between.  Here it does not:
+// a generation is four launches on one stream --
+//     breed  (ggs_breed.cu)   parents + fitness  -> children, written behind the elite rows
+//     decode + raster         children           -> their fitness
+//     select (below)          elitism, the new fitness vector, its stable ranking, the
+//                             (best, mean, median) curve point, best-so-far bookkeeping
+// -- and ggs_ga_run() enqueues as many generations as the caller asks for.  The host reads the
+// curves and the best individual when it wants them (ggs_ga_state), e.g. once per video frame.
+//
+// State lives in two generation buffers of [n_elite + P][N][9] floats used alternately: the
+// population of generation g is rows [0, P) of buffer g & 1 (elites first, then the first
+// P - n_elite children, algorithm.py:128-141).
+#include <math.h>
+
+#include <new>
+
+#include "ggs_common.cuh"
+
+namespace ggs {
+namespace {
+
+constexpr int kSelectThreads = 1024;
+constexpr int kMaxEnginePop = 16384;  // ranking sorts the population in one CTA's shared memory
+
+__device__ __forceinline__ unsigned sortable(float v)
+{
+    const unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+struct SelectParams {
+    const float *pop;        // current population  [P][N][9]   (rows [0,P) of its buffer)
+    const float *fit;        // its fitness         [P]
+    int *order;              // in: stable ascending ranking of `fit`; out: ranking of new_fit
+    float *next;             // next buffer [n_elite + keep ...][N][9]; children already at row n_elite
+    const float *child_fit;  // [keep]
+    float *new_fit;          // [P]
+    double *curve;           // this generation's (best, mean, median)
+    float *best_ind;         // [N][9]
+    double *best_fit;        // in / out
+    int *no_improve;         // in / out
+    int P, N, n_elite;
+};
+
+// One CTA.  Elitism (algorithm.py:128-141), ranking and statistics (algorithm.py:143-160).
+__global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams q)
+{
+    extern __shared__ __align__(16) unsigned long long s_key[];  // [P2] fitness key << 32 | index
+    __shared__ double s_sum[kSelectThreads / 32];
+    __shared__ int s_improved;
+    const int tid = threadIdx.x;
+    const int keep = q.P - q.n_elite;
+    const int64_t row = (int64_t)q.N * 9;
+
+    // elites survive unchanged, in rank order, at the front of the next population
+    for (int e = 0; e < q.n_elite; ++e) {
+        const int src = q.order[e];
+        const float *from = q.pop + src * row;
+        float *to = q.next + e * row;
+        for (int64_t i = tid; i < row; i += kSelectThreads) to[i] = from[i];
+        if (tid == 0) q.new_fit[e] = q.fit[src];
+    }
+    for (int i = tid; i < keep; i += kSelectThreads) q.new_fit[q.n_elite + i] = q.child_fit[i];
+    __syncthreads();  // new_fit (and order, read above) settled before the ranking overwrites
+
+    // stable ascending ranking: the index in the low word makes every key distinct
+    int P2 = 1;
+    while (P2 < q.P) P2 <<= 1;
+    for (int i = tid; i < P2; i += kSelectThreads)
+        s_key[i] = (i < q.P) ? (((unsigned long long)sortable(q.new_fit[i]) << 32) | (unsigned)i)
+                             : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= P2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < P2; i += kSelectThreads) {
+                const int partner = i ^ j;
+                if (partner > i) {
+                    const unsigned long long a = s_key[i], b = s_key[partner];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        s_key[i] = b;
+                        s_key[partner] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    double part = 0.0;
+    for (int i = tid; i < q.P; i += kSelectThreads) {
+        const int idx = (int)(s_key[i] & 0xffffffffull);
+        q.order[i] = idx;
+        part += (double)q.new_fit[idx];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((tid & 31) == 0) s_sum[tid >> 5] = part;
+    __syncthreads();
+    if (tid == 0) {
+        double sum = 0.0;
+        for (int w = 0; w < kSelectThreads / 32; ++w) sum += s_sum[w];
+        const double best = (double)q.new_fit[(int)(s_key[0] & 0xffffffffull)];
+        const double lo = (double)q.new_fit[(int)(s_key[(q.P - 1) / 2] & 0xffffffffull)];
+        const double hi = (double)q.new_fit[(int)(s_key[q.P / 2] & 0xffffffffull)];
+        q.curve[1] = sum / (double)q.P;
+        q.curve[2] = 0.5 * (lo + hi);  // statistics.median: mean of the middle two
+        // best so far (algorithm.py:150-155)
+        const bool improved = best + 1e-10 < *q.best_fit;
+        if (improved) {
+            *q.best_fit = best;
+            *q.no_improve = 0;
+        } else {
+            *q.no_improve += 1;
+        }
+        q.curve[0] = *q.best_fit;
+        s_improved = improved ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_improved) {
+        const float *from = q.next + (int64_t)(s_key[0] & 0xffffffffull) * row;
+        for (int64_t i = tid; i < row; i += kSelectThreads) q.best_ind[i] = from[i];
+    }
+}
+
+int fail(cudaError_t e, const char *what)
+{
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return GGS_ECUDA;
+}
+#define GGS_TRY(call)                                    \
+    do {                                                 \
+        cudaError_t e_ = (call);                         \
+        if (e_ != cudaSuccess) return fail(e_, #call);   \
+    } while (0)
+
+}  // namespace
+}  // namespace ggs
+
+using namespace ggs;
+
+struct ggs_ga {
+    int device = 0;
+    int P = 0, N = 0, H = 0, W = 0, n_elite = 0, capacity = 0;  // capacity: curve points
+    float *room[2] = {nullptr, nullptr};  // generation buffers [n_elite + P][N][9]
+    float *fit[2] = {nullptr, nullptr};   // [P]
+    float *child_fit = nullptr;           // [P]
+    int *order = nullptr;                 // [P]
+    float *target = nullptr, *mask = nullptr;
+    int mode = GGS_MODE_PLAIN;
+    float beta = 1.0f, k_sigma = 3.0f;
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+    double *curves = nullptr;             // [capacity][3]
+    float *best_ind = nullptr;            // [N][9]
+    double *best_fit = nullptr;
+    int *no_improve = nullptr;
+    uint64_t seed = 0;
+    int cur = 0;          // buffer holding the current population
+    int generation = -1;  // generations completed; -1 until ggs_ga_start
+    bool has_target = false;
+};
+
+static int ga_rank(ggs_ga *g, int n_elite, int next_buf, cudaStream_t st)
+{
+    SelectParams q;
+    q.pop = g->room[g->cur];
+    q.fit = g->fit[g->cur];
+    q.order = g->order;
+    q.next = g->room[next_buf];
+    q.child_fit = g->child_fit;
+    q.new_fit = g->fit[next_buf];
+    q.curve = g->curves + (size_t)(g->generation + 1) * 3;
+    q.best_ind = g->best_ind;
+    q.best_fit = g->best_fit;
+    q.no_improve = g->no_improve;
+    q.P = g->P;
+    q.N = g->N;
+    q.n_elite = n_elite;
+    int P2 = 1;
+    while (P2 < g->P) P2 <<= 1;
+    const size_t smem = (size_t)P2 * sizeof(unsigned long long);
+    if (smem > 48 * 1024)
+        GGS_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+    select_kernel<<<1, kSelectThreads, smem, st>>>(q);
+    GGS_TRY(cudaGetLastError());
+    return GGS_OK;
+}
+
+extern "C" {
+
+int ggs_ga_create(int device, int P, int N, int H, int W, int n_elite, int max_generations,
+                  ggs_ga **out)
+{
+    if (out == nullptr) {
+        set_error("ggs_ga_create: out is NULL");
+        return GGS_EINVAL;
+    }
+    *out = nullptr;
+    if (P < 1 || P > kMaxEnginePop || N < 1 || H < 1 || W < 1 || H > GGS_MAX_SIDE || W > GGS_MAX_SIDE ||
+        n_elite < 0 || n_elite > P || max_generations < 0) {
+        set_error("ggs_ga_create: bad arguments (P=%d, at most %d; N=%d; %dx%d; n_elite=%d; "
+                  "max_generations=%d)", P, kMaxEnginePop, N, H, W, n_elite, max_generations);
+        return GGS_EINVAL;
+    }
+    int n = 0;
+    GGS_TRY(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) {
+        set_error("ggs_ga_create: device %d not visible (%d devices)", device, n);
+        return GGS_ENODEVICE;
+    }
+    GGS_TRY(cudaSetDevice(device));
+    ggs_ga *g = new (std::nothrow) ggs_ga();
+    if (!g) {
+        set_error("out of host memory");
+        return GGS_EINVAL;
+    }
+    g->device = device;
+    g->P = P;
+    g->N = N;
+    g->H = H;
+    g->W = W;
+    g->n_elite = n_elite;
+    g->capacity = max_generations + 1;
+    const size_t rows = (size_t)(n_elite + P) * N * 9 * sizeof(float);
+    g->ws_bytes = workspace_bytes(P, N, H, W);
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaMalloc(&g->room[i], rows);
+        if (e == cudaSuccess) e = cudaMalloc(&g->fit[i], (size_t)P * sizeof(float));
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&g->child_fit, (size_t)P * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&g->order, (size_t)P * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&g->target, (size_t)H * W * 3 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&g->mask, (size_t)H * W * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&g->ws, g->ws_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&g->curves, (size_t)g->capacity * 3 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&g->best_ind, (size_t)N * 9 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&g->best_fit, sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&g->no_improve, sizeof(int));
+    if (e != cudaSuccess) {
+        ggs_ga_destroy(g);
+        return fail(e, "ggs_ga_create: cudaMalloc");
+    }
+    *out = g;
+    return GGS_OK;
+}
+
+void ggs_ga_destroy(ggs_ga *g)
+{
+    if (!g) return;
+    cudaSetDevice(g->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; ++i) {
+        if (g->room[i]) cudaFree(g->room[i]);
+        if (g->fit[i]) cudaFree(g->fit[i]);
+    }
+    void *rest[] = {g->child_fit, g->order, g->target, g->mask, g->ws, g->curves, g->best_ind,
+                    g->best_fit, g->no_improve};
+    for (void *p : rest)
+        if (p) cudaFree(p);
+    delete g;
+}
+
+int ggs_ga_set_target(ggs_ga *g, const float *d_target, const float *d_mask, int mode,
+                      float boost_beta, float k_sigma, void *stream)
+{
+    if (!g || !d_target) {
+        set_error("ggs_ga_set_target: NULL argument");
+        return GGS_EINVAL;
+    }
+    if (mode < GGS_MODE_PLAIN || mode > GGS_MODE_BOOST || (mode != GGS_MODE_PLAIN && !d_mask)) {
+        set_error("ggs_ga_set_target: mode %d needs a mask", mode);
+        return GGS_EINVAL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GGS_TRY(cudaSetDevice(g->device));
+    GGS_TRY(cudaMemcpyAsync(g->target, d_target, (size_t)g->H * g->W * 3 * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
+    if (d_mask)
+        GGS_TRY(cudaMemcpyAsync(g->mask, d_mask, (size_t)g->H * g->W * sizeof(float),
+                                cudaMemcpyDeviceToDevice, st));
+    g->mode = mode;
+    g->beta = boost_beta;
+    g->k_sigma = k_sigma;
+    g->has_target = true;
+    return GGS_OK;
+}
+
+int ggs_ga_start(ggs_ga *g, const float *d_population, int cols, uint64_t seed, void *stream)
+{
+    if (!g || !d_population || cols < 9) {
+        set_error("ggs_ga_start: bad arguments");
+        return GGS_EINVAL;
+    }
+    if (!g->has_target) {
+        set_error("ggs_ga_start: call ggs_ga_set_target first");
+        return GGS_EINVAL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GGS_TRY(cudaSetDevice(g->device));
+    // generation 0: the given population (first 9 columns), evaluated and ranked
+    GGS_TRY(cudaMemcpy2DAsync(g->room[0], 9 * sizeof(float), d_population, (size_t)cols * sizeof(float),
+                              9 * sizeof(float), (size_t)g->P * g->N, cudaMemcpyDeviceToDevice, st));
+    const float bg[3] = {1.0f, 1.0f, 1.0f};
+    int rc = evaluate(g->room[0], GGS_LAYOUT_AXES_ANGLE, g->P, g->N, 9, g->H, g->W, g->k_sigma, bg,
+                      g->target, g->mode == GGS_MODE_PLAIN ? nullptr : g->mask, g->mode, g->beta,
+                      g->child_fit, nullptr, 0, g->ws, g->ws_bytes, st);
+    if (rc) return rc;
+    const double inf = INFINITY;
+    const int zero = 0;
+    GGS_TRY(cudaMemcpyAsync(g->best_fit, &inf, sizeof(double), cudaMemcpyHostToDevice, st));
+    GGS_TRY(cudaMemcpyAsync(g->no_improve, &zero, sizeof(int), cudaMemcpyHostToDevice, st));
+    g->seed = seed;
+    g->cur = 0;
+    g->generation = -1;
+    rc = ga_rank(g, 0, 0, st);  // no elites: new_fit = child_fit, rows already in place
+    if (rc) return rc;
+    g->generation = 0;
+    return GGS_OK;
+}
+
+int ggs_ga_run(ggs_ga *g, int count, const float *h_sigma6, int tour_k, float cxpb, float mutpb,
+               float log_scale_lo, float log_scale_hi, void *stream)
+{
+    if (!g || count < 0 || (count > 0 && !h_sigma6) || tour_k < 1) {
+        set_error("ggs_ga_run: bad arguments");
+        return GGS_EINVAL;
+    }
+    if (g->generation < 0) {
+        set_error("ggs_ga_run: call ggs_ga_start first");
+        return GGS_EINVAL;
+    }
+    if (g->generation + count >= g->capacity) {
+        set_error("ggs_ga_run: %d more generations exceed the %d the engine was created for",
+                  count, g->capacity - 1);
+        return GGS_EINVAL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GGS_TRY(cudaSetDevice(g->device));
+    const float bg[3] = {1.0f, 1.0f, 1.0f};
+    const int keep = g->P - g->n_elite;
+    const size_t row = (size_t)g->N * 9;
+    for (int k = 0; k < count; ++k) {
+        const int gen = g->generation + 1, nb = g->cur ^ 1;
+        float *children = g->room[nb] + (size_t)g->n_elite * row;
+        GGS_TRY(launch_breed(g->room[g->cur], g->fit[g->cur], g->P, g->N, 9, keep, children, tour_k,
+                             cxpb, mutpb, h_sigma6 + 6 * (size_t)k, log_scale_lo, log_scale_hi,
+                             g->seed, (uint32_t)gen, st));
+        int rc = evaluate(children, GGS_LAYOUT_AXES_ANGLE, keep, g->N, 9, g->H, g->W, g->k_sigma, bg,
+                          g->target, g->mode == GGS_MODE_PLAIN ? nullptr : g->mask, g->mode,
+                          g->beta, g->child_fit, nullptr, 0, g->ws, g->ws_bytes, st);
+        if (rc) return rc;
+        rc = ga_rank(g, g->n_elite, nb, st);
+        if (rc) return rc;
+        g->cur = nb;
+        g->generation = gen;
+    }
+    return GGS_OK;
+}
+
+int ggs_ga_state(ggs_ga *g, void *stream, int *h_generation, double *h_best_fitness,
+                 int *h_no_improve, double *h_curves3, int curves_from, float *h_best_individual)
+{
+    if (!g || g->generation < 0) {
+        set_error("ggs_ga_state: engine not started");
+        return GGS_EINVAL;
+    }
+    if (curves_from < 0 || curves_from > g->generation + 1) {
+        set_error("ggs_ga_state: curves_from %d outside [0, %d]", curves_from, g->generation + 1);
+        return GGS_EINVAL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GGS_TRY(cudaSetDevice(g->device));
+    if (h_best_fitness)
+        GGS_TRY(cudaMemcpyAsync(h_best_fitness, g->best_fit, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h_no_improve)
+        GGS_TRY(cudaMemcpyAsync(h_no_improve, g->no_improve, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (h_curves3 && curves_from <= g->generation)
+        GGS_TRY(cudaMemcpyAsync(h_curves3, g->curves + (size_t)curves_from * 3,
+                                (size_t)(g->generation + 1 - curves_from) * 3 * sizeof(double),
+                                cudaMemcpyDeviceToHost, st));
+    if (h_best_individual)
+        GGS_TRY(cudaMemcpyAsync(h_best_individual, g->best_ind, (size_t)g->N * 9 * sizeof(float),
+                                cudaMemcpyDeviceToHost, st));
+    GGS_TRY(cudaStreamSynchronize(st));
+    if (h_generation) *h_generation = g->generation;
+    return GGS_OK;
+}
+
+int ggs_ga_population(ggs_ga *g, const float **d_population, const float **d_fitness)
+{
+    if (!g || g->generation < 0) {
+        set_error("ggs_ga_population: engine not started");
+        return GGS_EINVAL;
+    }
+    if (d_population) *d_population = g->room[g->cur];
+    if (d_fitness) *d_fitness = g->fit[g->cur];
+    return GGS_OK;
+}
+
+}  // extern "C"

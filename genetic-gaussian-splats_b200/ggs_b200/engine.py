@@ -1,0 +1,113 @@
+"""GA generations enqueued back to back (ggs_ga_* in include/ggs_b200.h): breeding, evaluation,
+elitism, ranking and curve statistics all stay on the device; the host reads results when it
+wants them.  Counterpart of the generation loop of the reference's modules/algorithm.py:87-160.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .evaluator import SIGMA_ORDER, _as_f32, _cuda_device, _stream_ptr
+from .native import MODE_BOOST, MODE_MASK, MODE_PLAIN, check, lib
+
+MAX_POPULATION = 16384   # the ranking kernel sorts the population in one CTA's shared memory
+
+
+class _DeviceView:
+    """Zero-copy torch view of engine-owned device memory (__cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, shape: Tuple[int, ...]):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+class GaEngine:
+    """One GA run on one device.
+
+        eng = GaEngine(target, mask, H, W, P, N, n_elite, max_generations)
+        eng.start(population, seed)                 # generation 0
+        eng.run(sigma_rows, tour_k, cxpb, mutpb, log_lo, log_hi)   # enqueue len(sigma_rows) generations
+        st = eng.state()                            # sync; curves, best individual
+    """
+
+    def __init__(self, target: torch.Tensor, weight_mask: Optional[torch.Tensor], H: int, W: int,
+                 P: int, N: int, n_elite: int, max_generations: int, *, k_sigma: float = 3.0,
+                 boost_only: bool = False, boost_beta: float = 1.0, device=None):
+        self.device = _cuda_device(device if device is not None else target.device)
+        self.P, self.N, self.H, self.W = int(P), int(N), int(H), int(W)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().ggs_ga_create(self.device.index or 0, self.P, self.N, self.H, self.W,
+                                      int(n_elite), int(max_generations), ctypes.byref(self._h)),
+                  "ggs_ga_create")
+            t = _as_f32(target, self.device)
+            assert t.shape == (self.H, self.W, 3), "target must be [H, W, 3]"
+            m = None if weight_mask is None else _as_f32(weight_mask, self.device)
+            assert m is None or m.shape == (self.H, self.W), "weight_mask must be [H, W]"
+            mode = MODE_PLAIN if m is None else (MODE_BOOST if boost_only else MODE_MASK)
+            check(lib().ggs_ga_set_target(self._h, t.data_ptr(), None if m is None else m.data_ptr(),
+                                          mode, float(boost_beta), float(k_sigma),
+                                          _stream_ptr(self.device)), "ggs_ga_set_target")
+            torch.cuda.current_stream(self.device).synchronize()   # t / m may be temporaries
+
+    def start(self, population: torch.Tensor, seed: int) -> None:
+        pop = _as_f32(population, self.device)
+        assert pop.shape[:2] == (self.P, self.N) and pop.shape[2] >= 9
+        with torch.cuda.device(self.device):
+            check(lib().ggs_ga_start(self._h, pop.data_ptr(), int(pop.shape[2]),
+                                     int(seed) & (2**64 - 1), _stream_ptr(self.device)), "ggs_ga_start")
+            torch.cuda.current_stream(self.device).synchronize()   # `pop` may be a temporary
+
+    def run(self, sigma_rows: Sequence[dict], tour_k: int, cxpb: float, mutpb: float,
+            log_scale_lo: float, log_scale_hi: float) -> None:
+        """Enqueue one generation per row of `sigma_rows` (dicts keyed like MUT_SIGMA_MAX)."""
+        count = len(sigma_rows)
+        if count == 0:
+            return
+        flat = (ctypes.c_float * (6 * count))(*[float(r[k]) for r in sigma_rows for k in SIGMA_ORDER])
+        with torch.cuda.device(self.device):
+            check(lib().ggs_ga_run(self._h, count, flat, int(tour_k), float(cxpb), float(mutpb),
+                                   float(log_scale_lo), float(log_scale_hi),
+                                   _stream_ptr(self.device)), "ggs_ga_run")
+
+    def state(self, curves_from: int = 0, want_best: bool = True) -> dict:
+        """Synchronise and read: generation, best fitness, stale count, curve points
+        [curves_from ..] as an [k, 3] array (best so far, mean, median), best individual."""
+        gen, stale, best = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+        ind = np.empty((self.N, 9), dtype=np.float32) if want_best else None
+        # the curve buffer must hold every point up to the generation reached by queued work
+        done = ctypes.c_int()
+        with torch.cuda.device(self.device):
+            check(lib().ggs_ga_state(self._h, _stream_ptr(self.device), ctypes.byref(done), None, None,
+                                     None, 0, None), "ggs_ga_state")
+            curves = np.empty((max(done.value + 1 - curves_from, 0), 3), dtype=np.float64)
+            check(lib().ggs_ga_state(self._h, _stream_ptr(self.device), ctypes.byref(gen),
+                                     ctypes.byref(best), ctypes.byref(stale),
+                                     curves.ctypes.data if curves.size else None, int(curves_from),
+                                     None if ind is None else ind.ctypes.data), "ggs_ga_state")
+        return {"generation": gen.value, "best_fitness": best.value, "no_improve": stale.value,
+                "curves": curves,
+                "best_individual": None if ind is None else torch.from_numpy(ind)}
+
+    def population(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Copies of the current population [P,N,9] and its fitness [P] (device tensors)."""
+        p, f = ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib().ggs_ga_population(self._h, ctypes.byref(p), ctypes.byref(f)), "ggs_ga_population")
+        with torch.cuda.device(self.device):
+            pop = torch.as_tensor(_DeviceView(p.value, (self.P, self.N, 9)), device=self.device).clone()
+            fit = torch.as_tensor(_DeviceView(f.value, (self.P,)), device=self.device).clone()
+        return pop, fit
+
+    def close(self) -> None:
+        if self._h:
+            lib().ggs_ga_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

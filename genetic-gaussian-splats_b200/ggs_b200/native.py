@@ -42,6 +42,14 @@ SIGNATURES = {
     "ggs_probe_peaks": (_i, [ctypes.POINTER(_f)]),
     "ggs_ga_breed": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _f, _f, ctypes.POINTER(_f), _f, _f,
                           ctypes.c_uint64, ctypes.c_uint32, _vp]),
+    "ggs_ga_create": (_i, [_i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp)]),
+    "ggs_ga_destroy": (None, [_vp]),
+    "ggs_ga_set_target": (_i, [_vp, _vp, _vp, _i, _f, _f, _vp]),
+    "ggs_ga_start": (_i, [_vp, _vp, _i, ctypes.c_uint64, _vp]),
+    "ggs_ga_run": (_i, [_vp, _i, ctypes.POINTER(_f), _i, _f, _f, _f, _f, _vp]),
+    "ggs_ga_state": (_i, [_vp, _vp, ctypes.POINTER(_i), ctypes.POINTER(_d), ctypes.POINTER(_i), _vp,
+                          _i, _vp]),
+    "ggs_ga_population": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     "ggs_mask_workspace_bytes": (_sz, [_i, _i]),
     "ggs_importance_mask": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.POINTER(_i), _i, _d, _d, _d, _d, _i,
                                  _d, _vp, _vp, _sz, _vp]),

@@ -163,6 +163,43 @@ int ggs_ga_breed(const float *d_population, const float *d_fitness, int P, int N
                  float log_scale_lo, float log_scale_hi, uint64_t seed, uint32_t generation,
                  void *stream);
 
+/* ---- GA engine: generations without the host in the loop (section 8f "next" #1) ---- */
+
+/*
+ * The whole generation of algorithm.py:87-160 on the device: breeding (ggs_ga_breed's kernel),
+ * evaluation of the children (the fused render + fitness path), elitism (the n_elite best
+ * survive unchanged at the front of the next population, algorithm.py:128-141), the stable
+ * ranking of the new fitness vector, the (best so far, mean, median) curve point and the
+ * best-individual bookkeeping (algorithm.py:143-160).  ggs_ga_run only ENQUEUES work (four
+ * launches per generation on `stream`); nothing is copied to the host until ggs_ga_state.
+ * The engine owns its device memory (two generation buffers, target, mask, workspace, curves).
+ * Limits: P <= 16384 (the ranking sorts in one CTA's shared memory).
+ */
+typedef struct ggs_ga ggs_ga;
+int ggs_ga_create(int device, int P, int N, int H, int W, int n_elite, int max_generations,
+                  ggs_ga **out);
+void ggs_ga_destroy(ggs_ga *ga);
+/* d_target [H][W][3], d_mask [H][W] or NULL (device pointers, copied); mode / boost_beta /
+ * k_sigma as in ggs_fitness. */
+int ggs_ga_set_target(ggs_ga *ga, const float *d_target, const float *d_mask, int mode,
+                      float boost_beta, float k_sigma, void *stream);
+/* Generation 0: copies the population [P][N][cols] (axes-angle), evaluates and ranks it.
+ * `seed` keys the counter-based random streams of every later generation. */
+int ggs_ga_start(ggs_ga *ga, const float *d_population, int cols, uint64_t seed, void *stream);
+/* Enqueue `count` more generations.  h_sigma6: [count][6] annealed mutation sigmas, one row per
+ * generation in ggs_ga_breed's order (the schedule stays with the caller, utils.py:19-33);
+ * the other parameters as in ggs_ga_breed.  Does not synchronise. */
+int ggs_ga_run(ggs_ga *ga, int count, const float *h_sigma6, int tour_k, float cxpb, float mutpb,
+               float log_scale_lo, float log_scale_hi, void *stream);
+/* Synchronises `stream` and reports: generations completed, best fitness so far, generations
+ * since the last improvement, curve points [curves_from, generation] as (best, mean, median)
+ * triples, the best individual [N][9].  Any output pointer may be NULL. */
+int ggs_ga_state(ggs_ga *ga, void *stream, int *h_generation, double *h_best_fitness,
+                 int *h_no_improve, double *h_curves3, int curves_from, float *h_best_individual);
+/* Device pointers to the current population [P][N][9] and its fitness [P]; valid until the
+ * next ggs_ga_run. */
+int ggs_ga_population(ggs_ga *ga, const float **d_population, const float **d_fitness);
+
 /* ---- importance mask, the weight_mask input of the fitness ---- */
 
 /*
