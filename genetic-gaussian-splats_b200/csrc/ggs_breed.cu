@@ -503,7 +503,7 @@ cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int 
     q.P = P;
     q.N = N;
     q.cols = cols;
-    q.n_children = n_children < P ? n_children : P;
+    q.n_children = n_children;  // may exceed P: SA proposes many children of one individual
     q.tour_k = tour_k;
     q.cxpb = cxpb;
     const float thr = rintf(fminf(fmaxf(mutpb, 0.0f), 1.0f) * 65536.0f);

@@ -72,8 +72,9 @@ cudaError_t launch_raster(const Workspace &ws, int B, int N, int H, int W, const
                           unsigned long long *d_stats, cudaStream_t stream);
 
 // breed.cu
-// The step defines P children; only the first n_children are produced (counter-based streams:
-// child c is the same whatever n_children is).
+// Children [0, n_children) of the step are produced (counter-based streams: child c is the same
+// whatever n_children is); a GA generation defines P of them, SA asks for `tries` mutated
+// copies of a one-individual population.
 cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int N, int cols,
                          int n_children, float *d_offspring, int tour_k, float cxpb, float mutpb,
                          const float sigma6[6], float log_lo, float log_hi, uint64_t seed,

@@ -127,6 +127,57 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams q)
     }
 }
 
+// ---- simulated annealing: the Metropolis step of one iteration (annealing.py:125-137) ----------
+constexpr int kMaxTries = 64;
+
+struct MetropolisParams {
+    const float *cand;     // [tries][N][9] neighbours, all proposed from the current state
+    const float *energy;   // [tries]
+    float *current;        // [N][9]   in / out
+    float *best;           // [N][9]   in / out
+    double *e_current;     // in / out
+    double *e_best;        // in / out
+    double *curve;         // this iteration's (best, current)
+    double temperature;
+    double uniform[kMaxTries];  // one U[0,1) draw per try (used when the try is uphill)
+    int tries, N;
+};
+
+// One CTA.  Thread 0 applies the tries in order: accept when dE <= 0 or u < exp(-dE / T); the
+// best-so-far test follows every try as in the reference.  Then all threads move the rows.
+__global__ void __launch_bounds__(kSelectThreads) metropolis_kernel(MetropolisParams q)
+{
+    __shared__ int s_cur, s_best;
+    if (threadIdx.x == 0) {
+        double e_cur = *q.e_current, e_best = *q.e_best;
+        int cur = -1, best = -1;
+        for (int k = 0; k < q.tries; ++k) {
+            const double e_new = (double)q.energy[k];
+            const double dE = e_new - e_cur;
+            if (dE <= 0.0 || (q.temperature > 0.0 && q.uniform[k] < exp(-dE / q.temperature))) {
+                cur = k;
+                e_cur = e_new;
+            }
+            if (e_cur + 1e-12 < e_best) {
+                e_best = e_cur;
+                best = cur;
+            }
+        }
+        *q.e_current = e_cur;
+        *q.e_best = e_best;
+        q.curve[0] = e_best;
+        q.curve[1] = e_cur;
+        s_cur = cur;
+        s_best = best;
+    }
+    __syncthreads();
+    const int64_t row = (int64_t)q.N * 9;
+    if (s_best >= 0)
+        for (int64_t i = threadIdx.x; i < row; i += kSelectThreads) q.best[i] = q.cand[s_best * row + i];
+    if (s_cur >= 0)
+        for (int64_t i = threadIdx.x; i < row; i += kSelectThreads) q.current[i] = q.cand[s_cur * row + i];
+}
+
 int fail(cudaError_t e, const char *what)
 {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -401,6 +452,247 @@ int ggs_ga_population(ggs_ga *g, const float **d_population, const float **d_fit
     }
     if (d_population) *d_population = g->room[g->cur];
     if (d_fitness) *d_fitness = g->fit[g->cur];
+    return GGS_OK;
+}
+
+/* ---------------------------------------------------------------------------------------- */
+/* simulated annealing                                                                        */
+
+}  // extern "C"
+
+struct ggs_sa {
+    int device = 0;
+    int N = 0, H = 0, W = 0, tries = 0, capacity = 0;
+    float *current = nullptr, *best = nullptr;  // [N][9]
+    float *cand = nullptr;                       // [tries][N][9]
+    float *energy = nullptr;                     // [tries]
+    float *dummy_fit = nullptr;                  // [1] fitness of the single "parent"
+    float *target = nullptr, *mask = nullptr;
+    int mode = GGS_MODE_PLAIN;
+    float beta = 1.0f, k_sigma = 3.0f;
+    void *ws = nullptr;
+    size_t ws_bytes = 0;
+    double *curves = nullptr;  // [capacity][2]
+    double *e_current = nullptr, *e_best = nullptr;
+    uint64_t seed = 0;
+    int iteration = -1;
+    bool has_target = false;
+};
+
+extern "C" {
+
+int ggs_sa_create(int device, int N, int H, int W, int tries, int max_iterations, ggs_sa **out)
+{
+    if (out == nullptr) {
+        set_error("ggs_sa_create: out is NULL");
+        return GGS_EINVAL;
+    }
+    *out = nullptr;
+    if (N < 1 || H < 1 || W < 1 || H > GGS_MAX_SIDE || W > GGS_MAX_SIDE || tries < 1 ||
+        tries > kMaxTries || max_iterations < 0) {
+        set_error("ggs_sa_create: bad arguments (N=%d; %dx%d; tries=%d, at most %d; "
+                  "max_iterations=%d)", N, H, W, tries, kMaxTries, max_iterations);
+        return GGS_EINVAL;
+    }
+    int n = 0;
+    GGS_TRY(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) {
+        set_error("ggs_sa_create: device %d not visible (%d devices)", device, n);
+        return GGS_ENODEVICE;
+    }
+    GGS_TRY(cudaSetDevice(device));
+    ggs_sa *g = new (std::nothrow) ggs_sa();
+    if (!g) {
+        set_error("out of host memory");
+        return GGS_EINVAL;
+    }
+    g->device = device;
+    g->N = N;
+    g->H = H;
+    g->W = W;
+    g->tries = tries;
+    g->capacity = max_iterations + 1;
+    const size_t row = (size_t)N * 9 * sizeof(float);
+    g->ws_bytes = workspace_bytes(tries, N, H, W);
+    cudaError_t e = cudaMalloc(&g->current, row);
+    if (e == cudaSuccess) e = cudaMalloc(&g->best, row);
+    if (e == cudaSuccess) e = cudaMalloc(&g->cand, row * tries);
+    if (e == cudaSuccess) e = cudaMalloc(&g->energy, (size_t)tries * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&g->dummy_fit, sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(g->dummy_fit, 0, sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&g->target, (size_t)H * W * 3 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&g->mask, (size_t)H * W * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&g->ws, g->ws_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&g->curves, (size_t)g->capacity * 2 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&g->e_current, sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&g->e_best, sizeof(double));
+    if (e != cudaSuccess) {
+        ggs_sa_destroy(g);
+        return fail(e, "ggs_sa_create: cudaMalloc");
+    }
+    *out = g;
+    return GGS_OK;
+}
+
+void ggs_sa_destroy(ggs_sa *g)
+{
+    if (!g) return;
+    cudaSetDevice(g->device);
+    cudaDeviceSynchronize();
+    void *all[] = {g->current, g->best, g->cand, g->energy, g->dummy_fit, g->target, g->mask, g->ws,
+                   g->curves, g->e_current, g->e_best};
+    for (void *p : all)
+        if (p) cudaFree(p);
+    delete g;
+}
+
+int ggs_sa_set_target(ggs_sa *g, const float *d_target, const float *d_mask, int mode,
+                      float boost_beta, float k_sigma, void *stream)
+{
+    if (!g || !d_target) {
+        set_error("ggs_sa_set_target: NULL argument");
+        return GGS_EINVAL;
+    }
+    if (mode < GGS_MODE_PLAIN || mode > GGS_MODE_BOOST || (mode != GGS_MODE_PLAIN && !d_mask)) {
+        set_error("ggs_sa_set_target: mode %d needs a mask", mode);
+        return GGS_EINVAL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GGS_TRY(cudaSetDevice(g->device));
+    GGS_TRY(cudaMemcpyAsync(g->target, d_target, (size_t)g->H * g->W * 3 * sizeof(float),
+                            cudaMemcpyDeviceToDevice, st));
+    if (d_mask)
+        GGS_TRY(cudaMemcpyAsync(g->mask, d_mask, (size_t)g->H * g->W * sizeof(float),
+                                cudaMemcpyDeviceToDevice, st));
+    g->mode = mode;
+    g->beta = boost_beta;
+    g->k_sigma = k_sigma;
+    g->has_target = true;
+    return GGS_OK;
+}
+
+static int sa_energy(ggs_sa *g, const float *genomes, int B, cudaStream_t st)
+{
+    const float bg[3] = {1.0f, 1.0f, 1.0f};
+    return evaluate(genomes, GGS_LAYOUT_AXES_ANGLE, B, g->N, 9, g->H, g->W, g->k_sigma, bg, g->target,
+                    g->mode == GGS_MODE_PLAIN ? nullptr : g->mask, g->mode, g->beta, g->energy,
+                    nullptr, 0, g->ws, g->ws_bytes, st);
+}
+
+int ggs_sa_start(ggs_sa *g, const float *d_state, int cols, uint64_t seed, void *stream)
+{
+    if (!g || !d_state || cols < 9) {
+        set_error("ggs_sa_start: bad arguments");
+        return GGS_EINVAL;
+    }
+    if (!g->has_target) {
+        set_error("ggs_sa_start: call ggs_sa_set_target first");
+        return GGS_EINVAL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GGS_TRY(cudaSetDevice(g->device));
+    // iteration 0: the given state is the current and the best one; its energy opens the curves.
+    // It is staged as candidate 0 and "accepted" by the Metropolis kernel (dE = -inf).
+    GGS_TRY(cudaMemcpy2DAsync(g->cand, 9 * sizeof(float), d_state, (size_t)cols * sizeof(float),
+                              9 * sizeof(float), (size_t)g->N, cudaMemcpyDeviceToDevice, st));
+    int rc = sa_energy(g, g->cand, 1, st);
+    if (rc) return rc;
+    const double inf = INFINITY;
+    GGS_TRY(cudaMemcpyAsync(g->e_current, &inf, sizeof(double), cudaMemcpyHostToDevice, st));
+    GGS_TRY(cudaMemcpyAsync(g->e_best, &inf, sizeof(double), cudaMemcpyHostToDevice, st));
+    MetropolisParams q = {};
+    q.cand = g->cand;
+    q.energy = g->energy;
+    q.current = g->current;
+    q.best = g->best;
+    q.e_current = g->e_current;
+    q.e_best = g->e_best;
+    q.curve = g->curves;
+    q.temperature = 0.0;
+    q.tries = 1;
+    q.N = g->N;
+    metropolis_kernel<<<1, kSelectThreads, 0, st>>>(q);
+    GGS_TRY(cudaGetLastError());
+    g->seed = seed;
+    g->iteration = 0;
+    return GGS_OK;
+}
+
+int ggs_sa_run(ggs_sa *g, int count, const float *h_sigma6, const double *h_temperature,
+               const double *h_uniform, float mutpb, float log_scale_lo, float log_scale_hi,
+               void *stream)
+{
+    if (!g || count < 0 || (count > 0 && (!h_sigma6 || !h_temperature || !h_uniform))) {
+        set_error("ggs_sa_run: bad arguments");
+        return GGS_EINVAL;
+    }
+    if (g->iteration < 0) {
+        set_error("ggs_sa_run: call ggs_sa_start first");
+        return GGS_EINVAL;
+    }
+    if (g->iteration + count >= g->capacity) {
+        set_error("ggs_sa_run: %d more iterations exceed the %d the engine was created for", count,
+                  g->capacity - 1);
+        return GGS_EINVAL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GGS_TRY(cudaSetDevice(g->device));
+    for (int k = 0; k < count; ++k) {
+        const int it = g->iteration + 1;
+        // `tries` independently mutated copies of the current state: the breeding kernel with a
+        // one-individual population and no crossover (annealing.py:121-128, batched)
+        GGS_TRY(launch_breed(g->current, g->dummy_fit, 1, g->N, 9, g->tries, g->cand, 1, 0.0f, mutpb,
+                             h_sigma6 + 6 * (size_t)k, log_scale_lo, log_scale_hi, g->seed,
+                             (uint32_t)it, st));
+        int rc = sa_energy(g, g->cand, g->tries, st);
+        if (rc) return rc;
+        MetropolisParams q = {};
+        q.cand = g->cand;
+        q.energy = g->energy;
+        q.current = g->current;
+        q.best = g->best;
+        q.e_current = g->e_current;
+        q.e_best = g->e_best;
+        q.curve = g->curves + (size_t)it * 2;
+        q.temperature = h_temperature[k];
+        for (int t = 0; t < g->tries; ++t) q.uniform[t] = h_uniform[(size_t)k * g->tries + t];
+        q.tries = g->tries;
+        q.N = g->N;
+        metropolis_kernel<<<1, kSelectThreads, 0, st>>>(q);
+        GGS_TRY(cudaGetLastError());
+        g->iteration = it;
+    }
+    return GGS_OK;
+}
+
+int ggs_sa_state(ggs_sa *g, void *stream, int *h_iteration, double *h_best_energy,
+                 double *h_current_energy, double *h_curves2, int curves_from, float *h_best_state,
+                 float *h_current_state)
+{
+    if (!g || g->iteration < 0) {
+        set_error("ggs_sa_state: engine not started");
+        return GGS_EINVAL;
+    }
+    if (curves_from < 0 || curves_from > g->iteration + 1) {
+        set_error("ggs_sa_state: curves_from %d outside [0, %d]", curves_from, g->iteration + 1);
+        return GGS_EINVAL;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GGS_TRY(cudaSetDevice(g->device));
+    const size_t row = (size_t)g->N * 9 * sizeof(float);
+    if (h_best_energy)
+        GGS_TRY(cudaMemcpyAsync(h_best_energy, g->e_best, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h_current_energy)
+        GGS_TRY(cudaMemcpyAsync(h_current_energy, g->e_current, sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h_curves2 && curves_from <= g->iteration)
+        GGS_TRY(cudaMemcpyAsync(h_curves2, g->curves + (size_t)curves_from * 2,
+                                (size_t)(g->iteration + 1 - curves_from) * 2 * sizeof(double),
+                                cudaMemcpyDeviceToHost, st));
+    if (h_best_state) GGS_TRY(cudaMemcpyAsync(h_best_state, g->best, row, cudaMemcpyDeviceToHost, st));
+    if (h_current_state)
+        GGS_TRY(cudaMemcpyAsync(h_current_state, g->current, row, cudaMemcpyDeviceToHost, st));
+    GGS_TRY(cudaStreamSynchronize(st));
+    if (h_iteration) *h_iteration = g->iteration;
     return GGS_OK;
 }
 

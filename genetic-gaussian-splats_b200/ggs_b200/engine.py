@@ -111,3 +111,94 @@ class GaEngine:
             self.close()
         except Exception:
             pass
+
+
+MAX_TRIES = 64   # ggs_sa_*: the Metropolis kernel takes one U[0,1) draw per try as a launch argument
+
+
+class SaEngine:
+    """One simulated-annealing chain on one device (ggs_sa_* in include/ggs_b200.h): the
+    iteration loop of the reference's modules/annealing.py:112-150 with batched neighbours.
+
+        eng = SaEngine(target, mask, H, W, N, tries, max_iterations)
+        eng.start(state, seed)                                    # iteration 0
+        eng.run(sigma_rows, temperatures, uniforms, mutpb, lo, hi) # enqueue len(sigma_rows) iterations
+        st = eng.state()                                          # sync; curves, best / current state
+    """
+
+    def __init__(self, target: torch.Tensor, weight_mask: Optional[torch.Tensor], H: int, W: int,
+                 N: int, tries: int, max_iterations: int, *, k_sigma: float = 3.0,
+                 boost_only: bool = False, boost_beta: float = 1.0, device=None):
+        self.device = _cuda_device(device if device is not None else target.device)
+        self.N, self.H, self.W, self.tries = int(N), int(H), int(W), int(tries)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().ggs_sa_create(self.device.index or 0, self.N, self.H, self.W, self.tries,
+                                      int(max_iterations), ctypes.byref(self._h)), "ggs_sa_create")
+            t = _as_f32(target, self.device)
+            assert t.shape == (self.H, self.W, 3), "target must be [H, W, 3]"
+            m = None if weight_mask is None else _as_f32(weight_mask, self.device)
+            assert m is None or m.shape == (self.H, self.W), "weight_mask must be [H, W]"
+            mode = MODE_PLAIN if m is None else (MODE_BOOST if boost_only else MODE_MASK)
+            check(lib().ggs_sa_set_target(self._h, t.data_ptr(), None if m is None else m.data_ptr(),
+                                          mode, float(boost_beta), float(k_sigma),
+                                          _stream_ptr(self.device)), "ggs_sa_set_target")
+            torch.cuda.current_stream(self.device).synchronize()   # t / m may be temporaries
+
+    def start(self, state: torch.Tensor, seed: int) -> None:
+        s = _as_f32(state, self.device)
+        assert s.dim() == 2 and s.shape[0] == self.N and s.shape[1] >= 9
+        with torch.cuda.device(self.device):
+            check(lib().ggs_sa_start(self._h, s.data_ptr(), int(s.shape[1]), int(seed) & (2**64 - 1),
+                                     _stream_ptr(self.device)), "ggs_sa_start")
+            torch.cuda.current_stream(self.device).synchronize()   # `s` may be a temporary
+
+    def run(self, sigma_rows: Sequence[dict], temperatures: Sequence[float],
+            uniforms: Sequence[Sequence[float]], mutpb: float, log_scale_lo: float,
+            log_scale_hi: float) -> None:
+        """Enqueue one iteration per row: its annealed sigmas (dict keyed like MUT_SIGMA_MAX), its
+        temperature and `tries` U[0,1) draws for the uphill tests."""
+        count = len(sigma_rows)
+        if count == 0:
+            return
+        assert len(temperatures) == count and len(uniforms) == count
+        sig = (ctypes.c_float * (6 * count))(*[float(r[k]) for r in sigma_rows for k in SIGMA_ORDER])
+        temp = (ctypes.c_double * count)(*[float(t) for t in temperatures])
+        uni = np.ascontiguousarray(np.asarray(uniforms, dtype=np.float64).reshape(count, self.tries))
+        with torch.cuda.device(self.device):
+            check(lib().ggs_sa_run(self._h, count, sig, temp,
+                                   uni.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), float(mutpb),
+                                   float(log_scale_lo), float(log_scale_hi),
+                                   _stream_ptr(self.device)), "ggs_sa_run")
+
+    def state(self, curves_from: int = 0, want_states: bool = True) -> dict:
+        """Synchronise and read: iteration, best / current energy, curve points [curves_from ..]
+        as a [k, 2] array (best, current), the best and the current state."""
+        it, e_best, e_cur = ctypes.c_int(), ctypes.c_double(), ctypes.c_double()
+        best = np.empty((self.N, 9), dtype=np.float32) if want_states else None
+        cur = np.empty((self.N, 9), dtype=np.float32) if want_states else None
+        done = ctypes.c_int()
+        with torch.cuda.device(self.device):
+            check(lib().ggs_sa_state(self._h, _stream_ptr(self.device), ctypes.byref(done), None, None,
+                                     None, 0, None, None), "ggs_sa_state")
+            curves = np.empty((max(done.value + 1 - curves_from, 0), 2), dtype=np.float64)
+            check(lib().ggs_sa_state(self._h, _stream_ptr(self.device), ctypes.byref(it),
+                                     ctypes.byref(e_best), ctypes.byref(e_cur),
+                                     curves.ctypes.data if curves.size else None, int(curves_from),
+                                     None if best is None else best.ctypes.data,
+                                     None if cur is None else cur.ctypes.data), "ggs_sa_state")
+        return {"iteration": it.value, "best_energy": e_best.value, "current_energy": e_cur.value,
+                "curves": curves,
+                "best_state": None if best is None else torch.from_numpy(best),
+                "current_state": None if cur is None else torch.from_numpy(cur)}
+
+    def close(self) -> None:
+        if self._h:
+            lib().ggs_sa_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -50,6 +50,14 @@ SIGNATURES = {
     "ggs_ga_state": (_i, [_vp, _vp, ctypes.POINTER(_i), ctypes.POINTER(_d), ctypes.POINTER(_i), _vp,
                           _i, _vp]),
     "ggs_ga_population": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    "ggs_sa_create": (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp)]),
+    "ggs_sa_destroy": (None, [_vp]),
+    "ggs_sa_set_target": (_i, [_vp, _vp, _vp, _i, _f, _f, _vp]),
+    "ggs_sa_start": (_i, [_vp, _vp, _i, ctypes.c_uint64, _vp]),
+    "ggs_sa_run": (_i, [_vp, _i, ctypes.POINTER(_f), ctypes.POINTER(_d), ctypes.POINTER(_d), _f, _f,
+                        _f, _vp]),
+    "ggs_sa_state": (_i, [_vp, _vp, ctypes.POINTER(_i), ctypes.POINTER(_d), ctypes.POINTER(_d), _vp,
+                          _i, _vp, _vp]),
     "ggs_mask_workspace_bytes": (_sz, [_i, _i]),
     "ggs_importance_mask": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.POINTER(_i), _i, _d, _d, _d, _d, _i,
                                  _d, _vp, _vp, _sz, _vp]),

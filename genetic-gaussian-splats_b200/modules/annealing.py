@@ -5,10 +5,13 @@ evaluation.  Here all tries of an iteration are proposed from the current state 
 in ONE launch (B = tries_per_iter, BASELINE config 2 "batched neighbour proposals"), then the
 Metropolis test is applied to them in order.  This changes the chain slightly -- a later try no
 longer starts from an earlier accepted try of the same iteration -- and is switched off with
-batch_neighbors=False, which reproduces the reference's sequential scheme."""
+batch_neighbors=False, which reproduces the reference's sequential scheme.  On one GPU the
+batched iterations run on the device engine (ggs_sa_run) without the host in the loop;
+GGS_B200_SA_LOOP=1 drives the same chain from Python instead (same result bit for bit)."""
 from __future__ import annotations
 
 import math
+import os
 import random
 from typing import Tuple
 
@@ -26,6 +29,7 @@ from modules.genetic import mutate_population
 from modules.mask import compute_importance_mask
 from modules.population import new_individual
 from ggs_b200 import breed
+from ggs_b200.engine import MAX_TRIES, SaEngine
 from modules.utils import (_anneal_factor, build_mut_sigma, prewarm_renderer, save_curves_csv,
                            save_frame_png, save_loss_curve_png, scale_log_bounds)
 
@@ -45,6 +49,99 @@ def _temp_schedule(kind: str, T0: float, i: int, total: int) -> float:
     if kind == "cauchy":
         return max(1e-12, T0 / (1.0 + i))
     return T0 * ((0.01 ** (1.0 / n)) ** i)   # "exp" and anything unknown
+
+
+def _iterations_on_engine(curr, target, imp_mask, H, W, k_sigma, boost_only, iterations, run_seed,
+                          temp0, temp_schedule, sigma_schedule, mut_sigma_max, mut_sigma_min, mutpb,
+                          min_scale_splats, max_scale_splats, tries, frame, frame_every, block=256):
+    """Iterations enqueued in blocks on the device engine (ggs_sa_run: propose, evaluate,
+    Metropolis -- four launches per iteration, no host sync); the host looks at the state once
+    per block, and at every frame boundary.  Same chain as _iterations_in_python with
+    batch_neighbors=True, bit for bit."""
+    lo, hi = scale_log_bounds(H, W, min_scale_splats, max_scale_splats)
+    eng = SaEngine(target, imp_mask, H, W, int(curr.shape[0]), tries, iterations, k_sigma=k_sigma,
+                   boost_only=boost_only)
+    try:
+        eng.start(curr, run_seed)
+        frame(0, eng.state()["best_state"])
+        pbar = tqdm(total=iterations, desc="SA iterations", leave=True)
+        it = 0
+        try:
+            while it < iterations:
+                stop = min(iterations, it + block)
+                if frame_every:
+                    stop = min(stop, (it // frame_every + 1) * frame_every)
+                steps = range(it, stop)
+                temps = [_temp_schedule(temp_schedule, temp0, i, iterations) for i in steps]
+                eng.run([build_mut_sigma(i, iterations, sigma_schedule, mut_sigma_max, mut_sigma_min)
+                         for i in steps], temps,
+                        [[random.random() for _ in range(tries)] for _ in steps], mutpb, lo, hi)
+                at_frame = bool(frame_every) and stop % frame_every == 0
+                st = eng.state(curves_from=stop, want_states=at_frame)
+                if at_frame:
+                    frame(stop, st["best_state"])
+                if hasattr(pbar, "update"):
+                    pbar.update(stop - it)
+                    pbar.set_postfix(best_mse=f"{st['best_energy']:.6f}",
+                                     curr_mse=f"{st['current_energy']:.6f}", T=f"{temps[-1]:.4g}",
+                                     sigma_fac=f"{_anneal_factor(stop - 1, iterations, sigma_schedule):.3f}")
+                it = stop
+        except KeyboardInterrupt:
+            print("\n[Interrupted] Returning current best...", flush=True)
+        finally:
+            if hasattr(pbar, "close"):
+                pbar.close()
+        st = eng.state()
+        c = st["curves"]
+        return st["best_state"], float(st["best_energy"]), {"best": c[:, 0].tolist(),
+                                                            "current": c[:, 1].tolist()}
+    finally:
+        eng.close()
+
+
+def _iterations_in_python(curr, energy, propose, iterations, temp0, temp_schedule, sigma_schedule,
+                          tries, batch_neighbors, frame, frame_every):
+    """The loop of annealing.py:112-150 driven from Python: the reference's sequential tries
+    (batch_neighbors=False), or the batched scheme one iteration at a time."""
+    e_curr = float(energy(curr.unsqueeze(0))[0])
+    best, best_fit = curr.clone(), e_curr
+    curves = {"best": [best_fit], "current": [e_curr]}
+    frame(0, best)
+    pbar = tqdm(range(iterations), desc="SA iterations", leave=True)
+    try:
+        for it in pbar:
+            T = _temp_schedule(temp_schedule, temp0, it, iterations)
+            accepted_any = False
+            if batch_neighbors:
+                neighbours = propose(curr, tries, it)
+                energies = energy(neighbours)
+                uniforms = [random.random() for _ in range(tries)]  # one per try, used if uphill
+            for k in range(tries):
+                if batch_neighbors:
+                    cand, e_new = neighbours[k], float(energies[k])
+                else:
+                    cand = propose(curr, 1, it)[0]
+                    e_new = float(energy(cand.unsqueeze(0))[0])
+                dE = e_new - e_curr
+                if dE <= 0.0 or (T > 0.0 and (uniforms[k] if batch_neighbors else random.random())
+                                 < math.exp(-dE / T)):
+                    curr, e_curr, accepted_any = cand.clone(), e_new, True
+                if e_curr + 1e-12 < best_fit:
+                    best_fit, best = e_curr, curr.clone()
+            curves["best"].append(best_fit)
+            curves["current"].append(e_curr)
+            if frame_every and (it + 1) % frame_every == 0:
+                frame(it + 1, best)
+            if hasattr(pbar, "set_postfix"):
+                pbar.set_postfix(best_mse=f"{best_fit:.6f}", curr_mse=f"{e_curr:.6f}", T=f"{T:.4g}",
+                                 accepted="Y" if accepted_any else "N",
+                                 sigma_fac=f"{_anneal_factor(it, iterations, sigma_schedule):.3f}")
+    except KeyboardInterrupt:
+        print("\n[Interrupted] Returning current best...", flush=True)
+    finally:
+        if hasattr(pbar, "close"):
+            pbar.close()
+    return best, best_fit, curves
 
 
 @torch.no_grad()
@@ -103,47 +200,24 @@ def simulated_annealing(
                                  mutpb, H, W, min_scale_splats, max_scale_splats)
 
     curr = new_individual(n_splats, H, W, min_scale_splats, max_scale_splats, device=device)
-    e_curr = float(energy(curr.unsqueeze(0))[0])
-    best, best_fit = curr.clone(), e_curr
-    curves = {"best": [best_fit], "current": [e_curr]}
-
-    pad = len(str(iterations))
-    if save_video:
-        save_frame_png(0, best, pad, prefix, video_dir, H, W, k_sigma, device, save_video)
-
     tries = max(1, tries_per_iter)
-    pbar = tqdm(range(iterations), desc="SA iterations", leave=True)
-    try:
-        for it in pbar:
-            T = _temp_schedule(temp_schedule, temp0, it, iterations)
-            accepted_any = False
-            if batch_neighbors:
-                neighbours = propose(curr, tries, it)
-                energies = energy(neighbours)
-            for k in range(tries):
-                if batch_neighbors:
-                    cand, e_new = neighbours[k], float(energies[k])
-                else:
-                    cand = propose(curr, 1, it)[0]
-                    e_new = float(energy(cand.unsqueeze(0))[0])
-                dE = e_new - e_curr
-                if dE <= 0.0 or (T > 0.0 and random.random() < math.exp(-dE / T)):
-                    curr, e_curr, accepted_any = cand.clone(), e_new, True
-                if e_curr + 1e-12 < best_fit:
-                    best_fit, best = e_curr, curr.clone()
-            curves["best"].append(best_fit)
-            curves["current"].append(e_curr)
-            if save_video and (it + 1) % max(1, frame_every) == 0:
-                save_frame_png(it + 1, best, pad, prefix, video_dir, H, W, k_sigma, device, save_video)
-            if hasattr(pbar, "set_postfix"):
-                pbar.set_postfix(best_mse=f"{best_fit:.6f}", curr_mse=f"{e_curr:.6f}", T=f"{T:.4g}",
-                                 accepted="Y" if accepted_any else "N",
-                                 sigma_fac=f"{_anneal_factor(it, iterations, sigma_schedule):.3f}")
-    except KeyboardInterrupt:
-        print("\n[Interrupted] Returning current best...", flush=True)
-    finally:
-        if hasattr(pbar, "close"):
-            pbar.close()
+    pad = len(str(iterations))
+
+    def frame(it: int, state: torch.Tensor) -> None:
+        if save_video:
+            save_frame_png(it, state.to(device), pad, prefix, video_dir, H, W, k_sigma, device,
+                           save_video)
+
+    if (batch_neighbors and curr.is_cuda and tries <= MAX_TRIES
+            and os.environ.get("GGS_B200_SA_LOOP", "0") != "1"):
+        best, best_fit, curves = _iterations_on_engine(
+            curr, target, imp_mask, H, W, k_sigma, boost_only, iterations, run_seed, temp0,
+            temp_schedule, sigma_schedule, mut_sigma_max, mut_sigma_min, mutpb, min_scale_splats,
+            max_scale_splats, tries, frame, max(1, frame_every) if save_video else 0)
+    else:
+        best, best_fit, curves = _iterations_in_python(
+            curr, energy, propose, iterations, temp0, temp_schedule, sigma_schedule, tries,
+            batch_neighbors, frame, max(1, frame_every) if save_video else 0)
 
     try:
         save_loss_curve_png(curves, loss_png_path, title=f"{prefix} energy (MSE)",

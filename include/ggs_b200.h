@@ -200,6 +200,40 @@ int ggs_ga_state(ggs_ga *ga, void *stream, int *h_generation, double *h_best_fit
  * next ggs_ga_run. */
 int ggs_ga_population(ggs_ga *ga, const float **d_population, const float **d_fitness);
 
+/* ---- simulated annealing on the device ---------------------- */
+
+/*
+ * The iteration loop of modules/annealing.py:112-150 with batched neighbour proposals
+ * (BASELINE config 2): per iteration `tries` independently mutated copies of the current state
+ * (the breeding kernel with a one-individual population and no crossover, annealing.py:121-128),
+ * ONE evaluation of all of them, and the Metropolis test applied to them in order
+ * (annealing.py:129-137: accept when dE <= 0 or u < exp(-dE / T); the best-so-far test follows
+ * every try).  ggs_sa_run only ENQUEUES work (four launches per iteration on `stream`); the
+ * temperature schedule, the annealed sigmas and the U[0,1) draws stay with the caller and are
+ * passed per iteration.  The engine owns its device memory.  Limits: tries <= 64.
+ */
+typedef struct ggs_sa ggs_sa;
+int ggs_sa_create(int device, int N, int H, int W, int tries, int max_iterations, ggs_sa **out);
+void ggs_sa_destroy(ggs_sa *sa);
+/* As ggs_ga_set_target. */
+int ggs_sa_set_target(ggs_sa *sa, const float *d_target, const float *d_mask, int mode,
+                      float boost_beta, float k_sigma, void *stream);
+/* Iteration 0: copies the state [N][cols] (axes-angle), evaluates it; it is the current and the
+ * best state (annealing.py:99-102).  `seed` keys the random streams of the proposals. */
+int ggs_sa_start(ggs_sa *sa, const float *d_state, int cols, uint64_t seed, void *stream);
+/* Enqueue `count` more iterations.  h_sigma6: [count][6] as in ggs_ga_run; h_temperature:
+ * [count]; h_uniform: [count][tries], the draw try k of that iteration compares with
+ * exp(-dE / T) when it is uphill.  Does not synchronise. */
+int ggs_sa_run(ggs_sa *sa, int count, const float *h_sigma6, const double *h_temperature,
+               const double *h_uniform, float mutpb, float log_scale_lo, float log_scale_hi,
+               void *stream);
+/* Synchronises `stream` and reports: iterations completed, best and current energy, curve
+ * points [curves_from, iteration] as (best, current) pairs, the best and the current state
+ * [N][9].  Any output pointer may be NULL. */
+int ggs_sa_state(ggs_sa *sa, void *stream, int *h_iteration, double *h_best_energy,
+                 double *h_current_energy, double *h_curves2, int curves_from, float *h_best_state,
+                 float *h_current_state);
+
 /* ---- importance mask, the weight_mask input of the fitness ---- */
 
 /*

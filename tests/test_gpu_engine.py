@@ -163,3 +163,127 @@ def test_genetic_approx_engine_equals_python_loop(ggs, tmp_path):
     # frames at generation 0, 16, 32 and the curve file with one line per generation
     assert len(list((tmp_path / "frames").glob("*.png"))) == 3
     assert len((tmp_path / "loss.csv").read_text().strip().splitlines()) == 40 + 2
+
+
+# ---- simulated annealing engine (ggs_sa_*) -----------------------------------------------------
+
+def host_sa_iteration(ggs, cur, e_cur, best, e_best, t, m, H, W, tries, it, seed, T, uniforms):
+    """One batched iteration with the public device ops; Metropolis on the host
+    (annealing.py:125-137)."""
+    nb = cur.unsqueeze(0).repeat(tries, 1, 1).contiguous()
+    cand = ggs.breed(nb, torch.zeros(tries, device="cuda"), SIG, tour_k=1, cxpb=0.0, mutpb=0.1,
+                     log_scale_lo=LO, log_scale_hi=HI, seed=seed, generation=it)
+    en = ggs.fitness(cand, t, H, W, 3.0, weight_mask=m).cpu().tolist()
+    for k in range(tries):
+        dE = en[k] - e_cur
+        if dE <= 0.0 or (T > 0.0 and uniforms[k] < math.exp(-dE / T)):
+            cur, e_cur = cand[k].clone(), en[k]
+        if e_cur + 1e-12 < e_best:
+            e_best, best = e_cur, cur.clone()
+    return cur, e_cur, best, e_best
+
+
+@pytest.mark.parametrize("N,tries,T0", [(40, 8, 2e-3), (33, 1, 1e-3), (12, 64, 5e-3), (25, 5, 0.0)])
+def test_sa_engine_iterations_match_host_metropolis(ggs, N, tries, T0):
+    from ggs_b200.engine import SaEngine
+    H, W, I, seed = 48, 64, 14, 31
+    pop, t, m = setup(1, N, H, W, seed=N)
+    rng = np.random.default_rng(tries)
+    eng = SaEngine(t, m, H, W, N, tries, I)
+    eng.start(pop[0], seed)
+    cur = pop[0].clone()
+    e_cur = float(ggs.fitness(pop, t, H, W, 3.0, weight_mask=m)[0])
+    best, e_best = cur.clone(), e_cur
+    st = eng.state()
+    assert st["iteration"] == 0 and st["best_energy"] == e_cur and st["current_energy"] == e_cur
+    assert torch.equal(st["best_state"], cur.cpu()) and torch.equal(st["current_state"], cur.cpu())
+    uphill_accepts = 0
+    for it in range(1, I + 1):
+        T = T0 * (1.0 - it / (I + 1))
+        u = rng.random(tries).tolist()
+        eng.run([SIG], [T], [u], 0.1, LO, HI)
+        before = e_cur
+        cur, e_cur, best, e_best = host_sa_iteration(ggs, cur, e_cur, best, e_best, t, m, H, W, tries,
+                                                     it, seed, T, u)
+        uphill_accepts += e_cur > before
+        st = eng.state(curves_from=it)
+        assert st["iteration"] == it
+        assert st["current_energy"] == e_cur and st["best_energy"] == e_best, it
+        assert torch.equal(st["current_state"], cur.cpu()), it
+        assert torch.equal(st["best_state"], best.cpu()), it
+        assert st["curves"].tolist() == [[e_best, e_cur]]
+    if T0 == 0.0:
+        assert uphill_accepts == 0
+    assert eng.state()["curves"].shape == (I + 1, 2)
+    eng.close()
+
+
+def test_sa_engine_blocks_equal_single_steps(ggs):
+    from ggs_b200.engine import SaEngine
+    N, H, W, I, tries = 50, 64, 64, 12, 6
+    pop, t, m = setup(1, N, H, W, seed=4)
+    rows = [{k: v * (1.0 - 0.05 * g) for k, v in SIG.items()} for g in range(I)]
+    temps = [3e-3 * (1.0 - g / I) for g in range(I)]
+    uni = np.random.default_rng(0).random((I, tries)).tolist()
+    out = []
+    for block in (I, 1, 5):
+        eng = SaEngine(t, None if block == 5 else m, H, W, N, tries, I)
+        eng.start(pop[0], 9)
+        for g0 in range(0, I, block):
+            eng.run(rows[g0:g0 + block], temps[g0:g0 + block], uni[g0:g0 + block], 0.1, LO, HI)
+        st = eng.state()
+        out.append((st["best_energy"], st["best_state"], st["curves"], st["current_state"]))
+        eng.close()
+    assert out[1][0] == out[0][0] and torch.equal(out[1][1], out[0][1])
+    assert np.array_equal(out[1][2], out[0][2]) and torch.equal(out[1][3], out[0][3])
+    assert out[2][0] != out[0][0]          # the plain (unmasked) energy is a different run
+
+
+def test_sa_engine_errors(ggs):
+    from ggs_b200.engine import SaEngine
+    pop, t, m = setup(1, 10, 32, 32)
+    with pytest.raises(ggs.GgsError):
+        SaEngine(t, m, 32, 32, 10, 65, 5)                 # more tries than the kernel takes
+    eng = SaEngine(t, m, 32, 32, 10, 2, 3)
+    with pytest.raises(ggs.GgsError):
+        eng.run([SIG], [1e-3], [[0.5, 0.5]], 0.1, LO, HI)  # not started
+    eng.start(pop[0], 3)
+    eng.run([SIG] * 3, [1e-3] * 3, [[0.5, 0.5]] * 3, 0.1, LO, HI)
+    with pytest.raises(ggs.GgsError):
+        eng.run([SIG], [1e-3], [[0.5, 0.5]], 0.1, LO, HI)  # beyond max_iterations
+    assert eng.state()["iteration"] == 3
+    eng.close()
+
+
+def test_simulated_annealing_engine_equals_python_loop(ggs, tmp_path):
+    """The SA entry point gives the same chain on the engine and on the Python-driven loop."""
+    import modules.config as C
+    from ggs_b200 import synth
+    from modules.annealing import simulated_annealing
+    import random
+    H, W = 48, 72
+    target = torch.from_numpy(synth.synthetic_target_np(H, W, 11))
+    kw = dict(H=H, W=W, device="cuda", n_splats=35, mutpb=0.05, mut_sigma_max=C.MUT_SIGMA_MAX,
+              mut_sigma_min=C.MUT_SIGMA_MIN, sigma_schedule="cosine", min_scale_splats=3.0,
+              max_scale_splats=0.1, k_sigma=3.0, mask_strength=0.7, boost_only=False, iterations=45,
+              temp0=2e-3, temp_schedule="cosine", tries_per_iter=8)
+    runs = []
+    for loop, frames in (("0", False), ("1", False), ("0", True)):
+        os.environ["GGS_B200_SA_LOOP"] = loop
+        os.environ["TQDM_DISABLE"] = "1"
+        try:
+            torch.manual_seed(3)
+            random.seed(5)
+            extra = {}
+            if frames:
+                d = tmp_path / "frames"
+                d.mkdir()
+                extra = dict(save_video=True, frame_every=16, video_dir=str(d), prefix="t",
+                             loss_csv_path=str(tmp_path / "loss.csv"))
+            runs.append(simulated_annealing(target, **kw, **extra))
+        finally:
+            os.environ.pop("GGS_B200_SA_LOOP", None)
+    for best, e in runs[1:]:
+        assert e == runs[0][1] and torch.equal(best, runs[0][0])
+    assert len(list((tmp_path / "frames").glob("*.png"))) == 3   # iteration 0, 16, 32
+    assert len((tmp_path / "loss.csv").read_text().strip().splitlines()) == 45 + 2
