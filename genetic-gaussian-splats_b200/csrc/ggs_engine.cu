@@ -33,10 +33,40 @@ __device__ __forceinline__ unsigned sortable(float v)
     return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// Copies one genome row with all of a thread's loads in flight before its first store (16-byte
+// accesses when both ends allow it): one memory round trip per 4 x blockDim float4s instead of
+// one per element.
+__device__ __forceinline__ void copy_row(float *__restrict__ to, const float *__restrict__ from,
+                                         int64_t n, int tid, int nthreads)
+{
+    int64_t done = 0;
+    if (((reinterpret_cast<uintptr_t>(to) | reinterpret_cast<uintptr_t>(from)) & 15u) == 0) {
+        const int64_t n4 = n >> 2;
+        const float4 *f4 = reinterpret_cast<const float4 *>(from);
+        float4 *t4 = reinterpret_cast<float4 *>(to);
+        for (int64_t base = 0; base < n4; base += 4 * (int64_t)nthreads) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = base + (int64_t)u * nthreads + tid;
+                if (i < n4) v[u] = f4[i];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = base + (int64_t)u * nthreads + tid;
+                if (i < n4) t4[i] = v[u];
+            }
+        }
+        done = n4 << 2;
+    }
+    for (int64_t i = done + tid; i < n; i += nthreads) to[i] = from[i];
+}
+
 struct SelectParams {
     const float *pop;        // current population  [P][N][9]   (rows [0,P) of its buffer)
     const float *fit;        // its fitness         [P]
-    int *order;              // in: stable ascending ranking of `fit`; out: ranking of new_fit
+    const int *order_in;     // stable ascending ranking of `fit`
+    int *order_out;          // ranking of new_fit (a different buffer: the copy CTAs read order_in)
     float *next;             // next buffer [n_elite + keep ...][N][9]; children already at row n_elite
     const float *child_fit;  // [keep]
     float *new_fit;          // [P]
@@ -47,7 +77,9 @@ struct SelectParams {
     int P, N, n_elite;
 };
 
-// One CTA.  Elitism (algorithm.py:128-141), ranking and statistics (algorithm.py:143-160).
+// Grid = 1 + n_elite CTAs.  CTA e + 1 copies elite e (the e-th best of the current generation,
+// algorithm.py:128-141) to the front of the next population; CTA 0 assembles the new fitness
+// vector, ranks it and keeps the statistics (algorithm.py:143-160).
 __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams q)
 {
     extern __shared__ __align__(16) unsigned long long s_key[];  // [P2] fitness key << 32 | index
@@ -57,16 +89,14 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams q)
     const int keep = q.P - q.n_elite;
     const int64_t row = (int64_t)q.N * 9;
 
-    // elites survive unchanged, in rank order, at the front of the next population
-    for (int e = 0; e < q.n_elite; ++e) {
-        const int src = q.order[e];
-        const float *from = q.pop + src * row;
-        float *to = q.next + e * row;
-        for (int64_t i = tid; i < row; i += kSelectThreads) to[i] = from[i];
-        if (tid == 0) q.new_fit[e] = q.fit[src];
+    if (blockIdx.x > 0) {  // elites survive unchanged, in rank order
+        const int e = blockIdx.x - 1;
+        copy_row(q.next + e * row, q.pop + q.order_in[e] * row, row, tid, kSelectThreads);
+        return;
     }
+    for (int e = tid; e < q.n_elite; e += kSelectThreads) q.new_fit[e] = q.fit[q.order_in[e]];
     for (int i = tid; i < keep; i += kSelectThreads) q.new_fit[q.n_elite + i] = q.child_fit[i];
-    __syncthreads();  // new_fit (and order, read above) settled before the ranking overwrites
+    __syncthreads();
 
     // stable ascending ranking: the index in the low word makes every key distinct
     int P2 = 1;
@@ -94,7 +124,7 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams q)
     double part = 0.0;
     for (int i = tid; i < q.P; i += kSelectThreads) {
         const int idx = (int)(s_key[i] & 0xffffffffull);
-        q.order[i] = idx;
+        q.order_out[i] = idx;
         part += (double)q.new_fit[idx];
     }
 #pragma unroll
@@ -122,8 +152,10 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams q)
     }
     __syncthreads();
     if (s_improved) {
-        const float *from = q.next + (int64_t)(s_key[0] & 0xffffffffull) * row;
-        for (int64_t i = tid; i < row; i += kSelectThreads) q.best_ind[i] = from[i];
+        // an elite row of `next` may still be in flight in its copy CTA: read its source instead
+        const int idx = (int)(s_key[0] & 0xffffffffull);
+        const float *from = (idx < q.n_elite) ? q.pop + q.order_in[idx] * row : q.next + idx * row;
+        copy_row(q.best_ind, from, row, tid, kSelectThreads);
     }
 }
 
@@ -172,10 +204,8 @@ __global__ void __launch_bounds__(kSelectThreads) metropolis_kernel(MetropolisPa
     }
     __syncthreads();
     const int64_t row = (int64_t)q.N * 9;
-    if (s_best >= 0)
-        for (int64_t i = threadIdx.x; i < row; i += kSelectThreads) q.best[i] = q.cand[s_best * row + i];
-    if (s_cur >= 0)
-        for (int64_t i = threadIdx.x; i < row; i += kSelectThreads) q.current[i] = q.cand[s_cur * row + i];
+    if (s_best >= 0) copy_row(q.best, q.cand + s_best * row, row, threadIdx.x, kSelectThreads);
+    if (s_cur >= 0) copy_row(q.current, q.cand + s_cur * row, row, threadIdx.x, kSelectThreads);
 }
 
 int fail(cudaError_t e, const char *what)
@@ -200,7 +230,8 @@ struct ggs_ga {
     float *room[2] = {nullptr, nullptr};  // generation buffers [n_elite + P][N][9]
     float *fit[2] = {nullptr, nullptr};   // [P]
     float *child_fit = nullptr;           // [P]
-    int *order = nullptr;                 // [P]
+    int *order[2] = {nullptr, nullptr};   // [P] rankings, used alternately
+    int ord = 0;                          // which one ranks the current population
     float *target = nullptr, *mask = nullptr;
     int mode = GGS_MODE_PLAIN;
     float beta = 1.0f, k_sigma = 3.0f;
@@ -221,7 +252,8 @@ static int ga_rank(ggs_ga *g, int n_elite, int next_buf, cudaStream_t st)
     SelectParams q;
     q.pop = g->room[g->cur];
     q.fit = g->fit[g->cur];
-    q.order = g->order;
+    q.order_in = g->order[g->ord];
+    q.order_out = g->order[g->ord ^ 1];
     q.next = g->room[next_buf];
     q.child_fit = g->child_fit;
     q.new_fit = g->fit[next_buf];
@@ -238,8 +270,9 @@ static int ga_rank(ggs_ga *g, int n_elite, int next_buf, cudaStream_t st)
     if (smem > 48 * 1024)
         GGS_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
-    select_kernel<<<1, kSelectThreads, smem, st>>>(q);
+    select_kernel<<<1 + n_elite, kSelectThreads, smem, st>>>(q);
     GGS_TRY(cudaGetLastError());
+    g->ord ^= 1;
     return GGS_OK;
 }
 
@@ -286,7 +319,7 @@ int ggs_ga_create(int device, int P, int N, int H, int W, int n_elite, int max_g
         if (e == cudaSuccess) e = cudaMalloc(&g->fit[i], (size_t)P * sizeof(float));
     }
     if (e == cudaSuccess) e = cudaMalloc(&g->child_fit, (size_t)P * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&g->order, (size_t)P * sizeof(int));
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc(&g->order[i], (size_t)P * sizeof(int));
     if (e == cudaSuccess) e = cudaMalloc(&g->target, (size_t)H * W * 3 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&g->mask, (size_t)H * W * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&g->ws, g->ws_bytes);
@@ -311,7 +344,7 @@ void ggs_ga_destroy(ggs_ga *g)
         if (g->room[i]) cudaFree(g->room[i]);
         if (g->fit[i]) cudaFree(g->fit[i]);
     }
-    void *rest[] = {g->child_fit, g->order, g->target, g->mask, g->ws, g->curves, g->best_ind,
+    void *rest[] = {g->child_fit, g->order[0], g->order[1], g->target, g->mask, g->ws, g->curves, g->best_ind,
                     g->best_fit, g->no_improve};
     for (void *p : rest)
         if (p) cudaFree(p);
