@@ -69,8 +69,9 @@ def test_encode_vs_reference(ggs, golden):
     ref = golden["chol"]
     for col in (0, 1, 5, 6, 7, 8):
         assert np.array_equal(got[..., col], ref[..., col])
-    for col in (2, 3, 4):
+    for col in (2, 3):
         np.testing.assert_allclose(got[..., col], ref[..., col], rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(got[..., 4], ref[..., 4], rtol=2e-6, atol=5e-6)  # l21 cancels
 
 
 def test_decode_aabb_bit_exact_vs_reference(ggs, golden):
@@ -78,8 +79,12 @@ def test_decode_aabb_bit_exact_vs_reference(ggs, golden):
     got = to_np(ggs.decode(cuda(golden["chol"]), H, W, k, layout=ggs.LAYOUT_CHOLESKY))
     for key in ("x0", "x1", "y0", "y1"):
         assert np.array_equal(got[key], golden["dec_" + key]), key
-    for key in ("cx", "cy", "rc", "gc", "bc", "a"):
+    # gpu_* goldens come from torch CUDA, which turns x / 255.0 into x * (1 / 255): one ulp
+    scale_ulp = 1 if golden["name"].startswith("gpu_") else 0
+    for key in ("cx", "cy"):
         assert ulp_diff(got[key], golden["dec_" + key]).max() == 0, key
+    for key in ("rc", "gc", "bc", "a"):
+        assert ulp_diff(got[key], golden["dec_" + key]).max() <= scale_ulp, key
     # the conic goes through exp (libdevice here, SLEEF in the CPU-generated goldens) and
     # three more roundings: a few ulp, i.e. < 2e-6 relative
     for key in ("sxx", "sxy", "syy"):
@@ -95,7 +100,8 @@ def test_decode_from_axes_matches_reference_aabb(ggs, golden):
 
 def test_render_vs_reference_kernel(ggs, golden):
     H, W, k = int(golden["H"]), int(golden["W"]), float(golden["k_sigma"])
-    img = ggs.render(cuda(golden["chol"]), H, W, k).cpu().numpy()
+    n = len(golden["images"])   # gpu_* goldens keep the images of the first few candidates
+    img = ggs.render(cuda(golden["chol"][:n]), H, W, k).cpu().numpy()
     assert img.shape == golden["images"].shape and img.dtype == np.float32
     assert np.abs(img - golden["images"]).max() <= IMG_TOL
 
@@ -117,7 +123,8 @@ def test_fused_images_equal_render_entry(ggs, golden):
     H, W, k = int(golden["H"]), int(golden["W"]), float(golden["k_sigma"])
     a, t = cuda(golden["axes"]), cuda(golden["target"])
     fit, img = ggs.fitness(a, t, H, W, k, want_images=True)
-    assert np.abs(img.cpu().numpy() - golden["images"]).max() <= IMG_TOL
+    n = len(golden["images"])
+    assert np.abs(img.cpu().numpy()[:n] - golden["images"]).max() <= IMG_TOL
     fit2 = ggs.fitness(a, t, H, W, k)
     assert torch.equal(fit, fit2)  # image output does not perturb the reduction
 
@@ -292,7 +299,8 @@ def test_modules_entry_points(ggs, golden):
     G9 = genome_to_renderer_batched(axes)
     assert G9.shape == golden["chol"].shape
     img = render_splats_rgb_triton(G9, H, W, k_sigma=k, device="cuda", tile=32)
-    assert np.abs(img.cpu().numpy() - golden["images"]).max() <= IMG_TOL
+    n = len(golden["images"])
+    assert np.abs(img.cpu().numpy()[:n] - golden["images"]).max() <= IMG_TOL
     one = render_splats_rgb_triton(genome_to_renderer(axes[0]), H, W, k_sigma=k, device="cuda")
     assert one.shape == (1, H, W, 3)  # 2-D input keeps B = 1 (render.py:220-221)
     assert torch.equal(one[0], img[0])
@@ -449,7 +457,7 @@ def test_uint8_frames_match_the_reference_conversion(ggs, golden):
     expect = (f32.cpu().numpy() * 255.0).astype("uint8")
     assert np.array_equal(u8.cpu().numpy(), expect)
     ref8 = (golden["images"] * 255.0).astype("uint8").astype(np.int16)
-    assert np.abs(u8.cpu().numpy().astype(np.int16) - ref8).max() <= 1   # 1e-4 can cross a step
+    assert np.abs(u8.cpu().numpy().astype(np.int16)[:len(ref8)] - ref8).max() <= 1   # 1e-4 can cross a step
     frame = render_axes_angle_to_img(cuda(golden["axes"])[0], H, W, k, "cuda")
     assert frame.dtype == np.uint8 and frame.shape == (H, W, 3)
     assert np.abs(frame.astype(np.int16) - ref8[0]).max() <= 1

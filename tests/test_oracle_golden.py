@@ -1,5 +1,7 @@
 """Pin the CPU oracle (oracle/ggs_oracle.c) against fixtures produced by the reference
-itself (tests/golden/make_golden.py).  CPU only."""
+itself: tests/golden/make_golden.py (torch CPU + the Triton interpreter, in the build container)
+and tests/golden/make_gpu_golden.py (gpu_*.npz: the reference's real CUDA/Triton path on a B200;
+images are kept for the first few candidates only).  CPU only."""
 import numpy as np
 
 from oracle import oracle
@@ -24,8 +26,10 @@ def test_encode_matches_reference(golden):
     assert chol.shape == ref.shape
     for col in (0, 1, 5, 6, 7, 8):
         assert np.array_equal(chol[..., col], ref[..., col])
-    for col in (2, 3, 4):
+    for col in (2, 3):
         np.testing.assert_allclose(chol[..., col], ref[..., col], rtol=2e-6, atol=1e-6)
+    # l21 = (cos sin (sx^2 - sy^2)) / l11 cancels; torch CUDA's sin/cos differ from glibc's too
+    np.testing.assert_allclose(chol[..., 4], ref[..., 4], rtol=2e-6, atol=5e-6)
 
 
 def test_decode_aabb_bit_exact(golden):
@@ -36,7 +40,8 @@ def test_decode_aabb_bit_exact(golden):
     for key in INT_KEYS:
         assert np.array_equal(dec[key], golden["dec_" + key]), key
     for key in FLOAT_KEYS:
-        assert ulp_diff(dec[key], golden["dec_" + key]).max() <= 4, key
+        # exp: SLEEF (torch CPU), libdevice (torch CUDA), glibc (here); x/255 is x*(1/255) on CUDA
+        assert ulp_diff(dec[key], golden["dec_" + key]).max() <= 8, key
 
 
 def test_decode_after_own_encode_aabb(golden):
@@ -52,7 +57,7 @@ def test_render_matches_reference_kernel(golden):
     # render.py:204-252 through the reference Triton kernel (interpreter): <= 1e-4 abs
     # is the north-star bound; the dense restatement actually agrees to ~1e-6.
     H, W, k = int(golden["H"]), int(golden["W"]), float(golden["k_sigma"])
-    img = oracle.render(golden["chol"], H, W, k)
+    img = oracle.render(golden["chol"][:len(golden["images"])], H, W, k)
     err = np.abs(img - golden["images"]).max()
     assert err <= 2e-6, err
 
@@ -76,12 +81,12 @@ def test_masked_fitness_keeps_the_denominator_quirk(golden):
     d2 = (img - golden["target"][None].astype(np.float64)) ** 2
     quirk = (d2 * w[None, :, :, None]).sum(axis=(1, 2, 3)) / (w.sum() + 1e-12)
     got = oracle.fitness(golden["axes"], golden["target"], H, W, k, weight_mask=golden["mask"])
-    np.testing.assert_allclose(got, quirk, rtol=1e-5)
+    np.testing.assert_allclose(got[:len(img)], quirk, rtol=1e-5)
 
 
 def test_score_of_golden_images(golden):
     got = oracle.score(golden["images"], golden["target"])
-    np.testing.assert_allclose(got, golden["fit_plain"], rtol=2e-6)
+    np.testing.assert_allclose(got, golden["fit_plain"][:len(got)], rtol=2e-6)
 
 
 def test_rank_order_matches(golden):
