@@ -2,6 +2,7 @@
 // carving, launch sequencing and the host-buffer path.  No kernels live here.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -19,6 +20,14 @@ void set_error(const char *fmt, ...)
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled()
+{
+    // read on every launch (a getenv is nanoseconds next to a launch) so a test or a timing
+    // script can flip it inside one process
+    const char *v = getenv("GGS_B200_PDL");
+    return !(v != nullptr && v[0] == '0');
 }
 
 static int cuda_fail(cudaError_t e, const char *what)

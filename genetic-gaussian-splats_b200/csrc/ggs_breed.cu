@@ -223,6 +223,8 @@ __global__ void __launch_bounds__(kBreedThreads) breed_kernel(BreedParams q)
     const int tid = threadIdx.x, lane = tid & 31;
     const int pair = blockIdx.x;
     const int nchild = (2 * pair + 1 < q.n_children) ? 2 : 1;
+    pdl_wait();
+    pdl_trigger();
 
     if (tid == 0) {
         // two independent tournaments: a shuffled list of iid tournament winners paired up
@@ -527,11 +529,10 @@ cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int 
                                                  (int)staged_bytes);
             if (e != cudaSuccess) return e;
         }
-        breed_kernel<true><<<(q.n_children + 1) / 2, kBreedThreads, staged_bytes, stream>>>(q);
-    } else {
-        breed_kernel<false><<<(q.n_children + 1) / 2, kBreedThreads, 0, stream>>>(q);
+        return launch_kernel(breed_kernel<true>, (q.n_children + 1) / 2, kBreedThreads, staged_bytes,
+                             stream, q);
     }
-    return cudaGetLastError();
+    return launch_kernel(breed_kernel<false>, (q.n_children + 1) / 2, kBreedThreads, 0, stream, q);
 }
 
 }  // namespace ggs

@@ -92,6 +92,39 @@ cudaError_t probe_peaks(float *h_out5);
 
 void set_error(const char *fmt, ...);
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------
+// The kernels of an evaluation (decode -> raster) and of a GA / SA step (breed -> decode ->
+// raster -> select) are short at small populations, so the few microseconds between dependent
+// launches count.  Every kernel launched through launch_kernel() may be scheduled while its
+// predecessor in the stream is still draining; it executes pdl_wait() -- which returns once the
+// predecessor has completed and its writes are visible -- before it touches global memory, and
+// pdl_trigger() right after, so the same holds for its own successor.  Kernels that precede it
+// and know nothing of this (torch's) simply trigger at exit.  GGS_B200_PDL=0 switches back to
+// plain stream order (for A/B timing).
+bool pdl_enabled();  // api.cu
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+
+template <typename... P, typename... A>
+inline cudaError_t launch_kernel(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, A... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+#endif
+
 // api.cu: decode + raster on `stream`, the launch sequence behind every evaluation entry.
 int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
              float k_sigma, const float bg[3], const float *d_target, const float *d_mask,

@@ -152,6 +152,8 @@ decode_kernel(const float *__restrict__ genomes, int cols, int64_t rows, int H, 
               int n_counters)
 {
     extern __shared__ __align__(16) float sm[];
+    pdl_wait();
+    pdl_trigger();
     if (blockIdx.x == 0 && counters != nullptr)
         for (int i = threadIdx.x; i < n_counters; i += kDecodeThreads) counters[i] = 0;
 
@@ -220,6 +222,8 @@ __global__ void __launch_bounds__(kDecodeThreads)
 encode_kernel(const float *__restrict__ axes, int cols, int64_t rows, float *__restrict__ chol)
 {
     extern __shared__ __align__(16) float sm[];
+    pdl_wait();
+    pdl_trigger();
     float tmp[9];
     const float *g = stage_rows(axes, cols, rows, sm, tmp);
     if (g == nullptr) return;
@@ -257,12 +261,10 @@ cudaError_t launch_decode(const float *d_genomes, int layout, int64_t rows, int 
     const unsigned grid = (unsigned)((rows + kDecodeThreads - 1) / kDecodeThreads);
     const size_t smem = stage_bytes(cols);
     if (layout == GGS_LAYOUT_AXES_ANGLE)
-        decode_kernel<true><<<grid, kDecodeThreads, smem, stream>>>(
-            d_genomes, cols, rows, H, W, k_sigma, rec, aabb, raw_f, raw_i, counters, n_counters);
-    else
-        decode_kernel<false><<<grid, kDecodeThreads, smem, stream>>>(
-            d_genomes, cols, rows, H, W, k_sigma, rec, aabb, raw_f, raw_i, counters, n_counters);
-    return cudaGetLastError();
+        return launch_kernel(decode_kernel<true>, grid, kDecodeThreads, smem, stream, d_genomes, cols,
+                             rows, H, W, k_sigma, rec, aabb, raw_f, raw_i, counters, n_counters);
+    return launch_kernel(decode_kernel<false>, grid, kDecodeThreads, smem, stream, d_genomes, cols,
+                         rows, H, W, k_sigma, rec, aabb, raw_f, raw_i, counters, n_counters);
 }
 
 cudaError_t launch_encode(const float *d_axes, int64_t rows, int cols, float *d_chol,
@@ -270,8 +272,8 @@ cudaError_t launch_encode(const float *d_axes, int64_t rows, int cols, float *d_
 {
     if (rows <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)((rows + kDecodeThreads - 1) / kDecodeThreads);
-    encode_kernel<<<grid, kDecodeThreads, stage_bytes(cols), stream>>>(d_axes, cols, rows, d_chol);
-    return cudaGetLastError();
+    return launch_kernel(encode_kernel, grid, kDecodeThreads, stage_bytes(cols), stream, d_axes, cols,
+                         rows, d_chol);
 }
 
 }  // namespace ggs

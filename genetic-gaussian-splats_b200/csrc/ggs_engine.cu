@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams q)
     const int tid = threadIdx.x;
     const int keep = q.P - q.n_elite;
     const int64_t row = (int64_t)q.N * 9;
+    pdl_wait();
+    pdl_trigger();
 
     if (blockIdx.x > 0) {  // elites survive unchanged, in rank order
         const int e = blockIdx.x - 1;
@@ -180,6 +182,8 @@ struct MetropolisParams {
 __global__ void __launch_bounds__(kSelectThreads) metropolis_kernel(MetropolisParams q)
 {
     __shared__ int s_cur, s_best;
+    pdl_wait();
+    pdl_trigger();
     if (threadIdx.x == 0) {
         double e_cur = *q.e_current, e_best = *q.e_best;
         int cur = -1, best = -1;
@@ -270,8 +274,7 @@ static int ga_rank(ggs_ga *g, int n_elite, int next_buf, cudaStream_t st)
     if (smem > 48 * 1024)
         GGS_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
-    select_kernel<<<1 + n_elite, kSelectThreads, smem, st>>>(q);
-    GGS_TRY(cudaGetLastError());
+    GGS_TRY(launch_kernel(select_kernel, 1 + n_elite, kSelectThreads, smem, st, q));
     g->ord ^= 1;
     return GGS_OK;
 }
@@ -644,8 +647,7 @@ int ggs_sa_start(ggs_sa *g, const float *d_state, int cols, uint64_t seed, void 
     q.temperature = 0.0;
     q.tries = 1;
     q.N = g->N;
-    metropolis_kernel<<<1, kSelectThreads, 0, st>>>(q);
-    GGS_TRY(cudaGetLastError());
+    GGS_TRY(launch_kernel(metropolis_kernel, 1, kSelectThreads, 0, st, q));
     g->seed = seed;
     g->iteration = 0;
     return GGS_OK;
@@ -691,8 +693,7 @@ int ggs_sa_run(ggs_sa *g, int count, const float *h_sigma6, const double *h_temp
         for (int t = 0; t < g->tries; ++t) q.uniform[t] = h_uniform[(size_t)k * g->tries + t];
         q.tries = g->tries;
         q.N = g->N;
-        metropolis_kernel<<<1, kSelectThreads, 0, st>>>(q);
-        GGS_TRY(cudaGetLastError());
+        GGS_TRY(launch_kernel(metropolis_kernel, 1, kSelectThreads, 0, st, q));
         g->iteration = it;
     }
     return GGS_OK;

@@ -295,6 +295,8 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
 
     const float4 *recb = rec + (int64_t)b * N * 3;
     const uint2 *boxb = aabb + (int64_t)b * N;
+    pdl_wait();  // the decode launch ahead of us has completed; nothing above reads memory
+    pdl_trigger();
 
     // Walk the genome from its last splat to its first (front to back).  Slot j of a round
     // maps thread `tid` to record  top - 1 - (j*kThreads + tid): ascending (j, tid) is
@@ -492,16 +494,14 @@ cudaError_t launch_raster(const Workspace &ws, int B, int N, int H, int W, const
     const int64_t grid = (int64_t)B * ntiles;
     if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     if (d_stats != nullptr)
-        raster_kernel<true><<<(unsigned)grid, kThreads, 0, stream>>>(
-            ws.rec, ws.aabb, N, H, W, ntx, ntiles, bg[0], bg[1], bg[2], d_target, d_mask, mode,
-            beta, static_cast<float *>(d_images), image_u8, ws.partial, ws.counter, d_fitness,
-            d_stats);
-    else
-        raster_kernel<false><<<(unsigned)grid, kThreads, 0, stream>>>(
-            ws.rec, ws.aabb, N, H, W, ntx, ntiles, bg[0], bg[1], bg[2], d_target, d_mask, mode,
-            beta, static_cast<float *>(d_images), image_u8, ws.partial, ws.counter, d_fitness,
-            nullptr);
-    return cudaGetLastError();
+        return launch_kernel(raster_kernel<true>, (unsigned)grid, kThreads, 0, stream, ws.rec, ws.aabb,
+                             N, H, W, ntx, ntiles, bg[0], bg[1], bg[2], d_target, d_mask, mode, beta,
+                             static_cast<float *>(d_images), image_u8, ws.partial, ws.counter,
+                             d_fitness, d_stats);
+    return launch_kernel(raster_kernel<false>, (unsigned)grid, kThreads, 0, stream, ws.rec, ws.aabb, N,
+                         H, W, ntx, ntiles, bg[0], bg[1], bg[2], d_target, d_mask, mode, beta,
+                         static_cast<float *>(d_images), image_u8, ws.partial, ws.counter, d_fitness,
+                         nullptr);
 }
 
 }  // namespace ggs
