@@ -25,7 +25,10 @@ constexpr int kRowsPerThread = GGS_ROWS;
 constexpr int kWarps = GGS_WARPS;
 constexpr int kTileH = kWarps * kRowsPerThread;
 constexpr int kThreads = kWarps * 32;
-constexpr int kListCap = 512;  // staged splat records per flush (48 B each)
+#ifndef GGS_LIST_CAP
+#define GGS_LIST_CAP 512
+#endif
+constexpr int kListCap = GGS_LIST_CAP;  // staged splat records per flush (48 B each)
 
 constexpr int kDecodeThreads = 256;
 constexpr int kDecodeStageMaxCols = 16;

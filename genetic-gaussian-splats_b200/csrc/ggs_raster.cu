@@ -47,7 +47,11 @@ namespace {
 #endif
 
 constexpr int kPairs = kRowsPerThread / 2;
-constexpr int kScanPerThread = 256 / kThreads;          // 256 records examined per round
+#ifndef GGS_SCAN_CHUNK
+#define GGS_SCAN_CHUNK 256
+#endif
+constexpr int kScanPerThread = GGS_SCAN_CHUNK / kThreads;  // 256 records examined per round
+static_assert(GGS_SCAN_CHUNK <= kListCap, "a scan round must fit the list");
 constexpr int kScanChunk = kThreads * kScanPerThread;
 #ifndef GGS_SAT_EVERY
 #define GGS_SAT_EVERY 8

@@ -77,6 +77,43 @@ def run_side(path, inputs, repeats_scale):
     return out
 
 
+def run_search(path, target, gens_ga, iters_sa):
+    """genetic_approx / simulated_annealing of the checkout at `path`, at the reference's default
+    sizes (modules/config.py: 512 splats, population 32, 8 elites, 8 SA tries; work size 256x256
+    here).  Returns seconds per generation / iteration beyond a 0-generation run (set-up, mask,
+    initial population)."""
+    import random
+    use(path)
+    C = importlib.import_module("modules.config")
+    ga = importlib.import_module("modules.algorithm").genetic_approx
+    sa = importlib.import_module("modules.annealing").simulated_annealing
+    H = W = 256
+    common = dict(mut_sigma_max=C.MUT_SIGMA_MAX, mut_sigma_min=C.MUT_SIGMA_MIN,
+                  min_scale_splats=C.MIN_SCALE_SPLATS, max_scale_splats=C.MAX_SCALE_SPLATS,
+                  k_sigma=C.K_SIGMA, mask_strength=C.MASK_STRENGTH, boost_only=C.BOOST_ONLY)
+
+    def timed(fn, n):
+        out = []
+        for count in (0, 0, n):      # first call: warm-up (library load / Triton compile)
+            torch.manual_seed(C.SEED); random.seed(C.SEED)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            res = fn(count)
+            torch.cuda.synchronize(); out.append((time.perf_counter() - t0, res[1]))
+        return (out[2][0] - out[1][0]) / n, out[1][1], out[2][1]
+
+    ga_s, ga_f0, ga_f1 = timed(lambda n: ga(target, H, W, "cuda", pop_size=C.POP_SIZE, n_splats=C.N_SPLATS,
+                                            generations=n, tour_k=C.TOUR_K, elite_k=C.ELITE_K, cxpb=C.CXPB,
+                                            mutpb=C.MUTPB, schedule=C.SCHEDULE, **common), gens_ga)
+    sa_s, sa_f0, sa_f1 = timed(lambda n: sa(target, H, W, "cuda", n_splats=C.N_SPLATS, mutpb=C.MUTPB,
+                                            sigma_schedule=C.SCHEDULE, iterations=n, temp0=C.SA_T0,
+                                            temp_schedule=C.SA_SCHEDULE, tries_per_iter=C.SA_TRIES_PER_ITER,
+                                            **common), iters_sa)
+    print(f"  {os.path.basename(path)}: GA {1.0 / ga_s:.1f} generations/s ({ga_f0:.5f} -> {ga_f1:.5f} in "
+          f"{gens_ga}), SA {1.0 / sa_s:.1f} iterations/s ({sa_f0:.5f} -> {sa_f1:.5f} in {iters_sa})", flush=True)
+    return {"ga_generations_per_s": 1.0 / ga_s, "ga_generations_timed": gens_ga, "ga_fitness": [ga_f0, ga_f1],
+            "sa_iterations_per_s": 1.0 / sa_s, "sa_iterations_timed": iters_sa, "sa_energy": [sa_f0, sa_f1]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "reference_gpu_compare.json"))
@@ -120,6 +157,16 @@ def main():
         row["speedup"] = a_["seconds"] / b_["seconds"]
         rows.append(row)
         print(json.dumps(row), flush=True)
+    os.environ["TQDM_DISABLE"] = "1"
+    tgt = torch.from_numpy(synth.synthetic_target_np(256, 256, 9))
+    search = {"what": "genetic_approx / simulated_annealing entry points at the reference's default sizes "
+                      "(256x256 work size, 512 splats, population 32, 8 elites; SA 8 tries per iteration), "
+                      "marginal rate beyond a 0-generation run",
+              "reference": run_search(REF, tgt, 60, 60),
+              "this_library": run_search(OURS, tgt, 20000, 20000)}
+    search["ga_speedup"] = search["this_library"]["ga_generations_per_s"] / search["reference"]["ga_generations_per_s"]
+    search["sa_speedup"] = search["this_library"]["sa_iterations_per_s"] / search["reference"]["sa_iterations_per_s"]
+    print(json.dumps(search), flush=True)
     meta = {"gpu": torch.cuda.get_device_name(0), "torch": torch.__version__,
             "triton": importlib.import_module("triton").__version__,
             "what": "reference = unmodified josedelrey/genetic-gaussian-splats modules/ (Triton path) "
@@ -128,7 +175,7 @@ def main():
             "tolerances": {"image": 1e-4, "fitness_rel": 1e-5}}
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     with open(a.out, "w") as f:
-        json.dump({"meta": meta, "rows": rows}, f, indent=1)
+        json.dump({"meta": meta, "rows": rows, "search": search}, f, indent=1)
     print("wrote", a.out)
 
 
