@@ -80,6 +80,29 @@ def ncu_traffic(workload: str, population: int):
     return best
 
 
+def reference_gpu_recorded(workload: str):
+    """The reference's real Triton path on a B200, as RECORDED by tools/reference_gpu_compare.py
+    (profiles/rNN_reference_gpu_compare.json): it cannot run inside bench.py (the reference is
+    not on the GPU box).  Context for the reader, not a live measurement."""
+    tag = {"c1": "config 1", "c2": "config 2", "c3": "config 3"}.get(workload)
+    pdir = os.path.join(ROOT, "profiles")
+    found = None
+    for name in sorted(os.listdir(pdir)) if (tag and os.path.isdir(pdir)) else []:
+        if name.endswith("_reference_gpu_compare.json"):
+            try:
+                rec = json.load(open(os.path.join(pdir, name)))
+            except Exception:
+                continue
+            for row in rec.get("rows", []):
+                if row.get("shape", "").startswith(tag):
+                    found = {"value": row["reference_candidates_per_s"], "unit": UNIT,
+                             "ms_per_call": row["reference_ms_per_call"],
+                             "candidates_per_call": row["candidates"], "source": "profiles/" + name,
+                             "what": "unmodified reference (Triton) through fitness_population on "
+                                     "one B200, recorded run, wall clock"}
+    return found
+
+
 def dist_env():
     return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
             int(os.environ.get("WORLD_SIZE", "1")))
@@ -377,6 +400,7 @@ def run_ours(args, wl):
                     "api": "ggs_ctx_fitness_host (C ABI, pinned host genomes in, host fitness out)"},
             "gpu_launches": 2 * K,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "reference_gpu_recorded": reference_gpu_recorded(args.workload) if world == 1 else None,
         }
         emit(line)
     if world > 1:
