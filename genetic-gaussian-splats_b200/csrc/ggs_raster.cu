@@ -59,6 +59,12 @@ constexpr int kScanChunk = kThreads * kScanPerThread;
 #ifndef GGS_BOX_PREFETCH
 #define GGS_BOX_PREFETCH 1
 #endif
+#ifndef GGS_DENSE_STAGE
+#define GGS_DENSE_STAGE 1
+#endif
+#if GGS_DENSE_STAGE && !GGS_BOX_PREFETCH
+#error "GGS_DENSE_STAGE needs GGS_BOX_PREFETCH"
+#endif
 constexpr int kSatEvery = GGS_SAT_EVERY;                 // list entries between saturation votes
 constexpr float kOpaque = 2.384185791015625e-07f;        // 2^-22: transmittance counted as zero
 static_assert(kScanPerThread >= 1, "at most 256 threads per CTA");
@@ -146,19 +152,24 @@ __device__ __forceinline__ f2_t add2(f2_t a, f2_t b)
 //   q0 = cx, cy, A, Bq      q1 = Cq, la, r, g      q2 = b, lane mask, row code, h
 // lane mask: bit l set iff column X0+l lies in [x0, x1].
 // row code : byte w describes band w: 0x0f = not touched, else lo | hi << 4 (rows lo..hi of the
-//            band are inside [y0, y1]); (R-1) << 4 = all rows, the only value that may take the
-//            recurrence path (and only for a gentle splat, h >= 0).
+//            band are inside [y0, y1]), bit 7 set for a steep splat (h < 0); (R-1) << 4 = all
+//            rows of a gentle splat, the only value that takes the recurrence path.
 constexpr unsigned kBandMiss = 0x0fu;
 constexpr unsigned kBandFull = (unsigned)(kRowsPerThread - 1) << 4;
 
-__device__ __forceinline__ unsigned row_code(int y0, int y1, int Y0)
+// With 8 rows per thread hi needs 3 bits, and bit 7 of a touched band's byte flags a steep splat:
+// "byte == kBandFull" is then the whole test for the recurrence path.
+constexpr unsigned kSteepBit = (kRowsPerThread == 8) ? 0x80u : 0u;
+
+__device__ __forceinline__ unsigned row_code(int y0, int y1, int Y0, bool steep)
 {
     unsigned code = 0;
+    const unsigned flag = steep ? kSteepBit : 0u;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) {
         const int yb = Y0 + w * kRowsPerThread;
         const int lo = max(y0 - yb, 0), hi = min(y1 - yb, kRowsPerThread - 1);
-        const unsigned c = (lo > hi) ? kBandMiss : (unsigned)(lo | (hi << 4));
+        const unsigned c = (lo > hi) ? kBandMiss : ((unsigned)(lo | (hi << 4)) | flag);
         code |= c << (8 * w);
     }
     return code;
@@ -219,7 +230,7 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
         const f2_t QY = pack2(dy, dy + 1.0f);
         const f2_t CQ2 = bcast2(q1.x), T12 = bcast2(t1), T02 = bcast2(t0);
         const f2_t R2 = bcast2(q1.z), G2 = bcast2(q1.w), B2 = bcast2(q2.x);
-        if (c == kBandFull && q2.w >= 0.0f) {
+        if (c == kBandFull && (kSteepBit != 0u || q2.w >= 0.0f)) {
             const f2_t E = fma2(fma2(CQ2, QY, T12), QY, T02);
             const float c4 = 4.0f * q1.x;
             const f2_t D = fma2(bcast2(c4), QY, bcast2(fmaf(2.0f, t1, c4)));  // e(i+2) - e(i)
@@ -239,7 +250,7 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
             GGS_PAIRS(GGS_RECUR_PAIR)
 #undef GGS_RECUR_PAIR
         } else {
-            const int lo = (int)(c & 15u), hi = (int)(c >> 4);
+            const int lo = (int)(c & 15u), hi = (int)((c & ~kSteepBit) >> 4);
 #define GGS_EXACT_PAIR(k)                                                          \
     if (2 * k + 1 >= lo && 2 * k <= hi) {                                          \
         const f2_t QYk = add2(QY, bcast2((float)(2 * k)));                         \
@@ -270,7 +281,12 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
 {
     unsigned work[2] = {0u, 0u};  // kStats: row pairs blended on the recurrence / exact path
     __shared__ float4 s_list[kListCap * 3];
+#if GGS_DENSE_STAGE
+    __shared__ int s_wcnt[2][kScanPerThread][kWarps];
+    __shared__ int s_idx[kListCap];
+#else
     __shared__ int s_wcnt[kScanPerThread][kWarps];
+#endif
     __shared__ float s_red[2 * kWarps];
     __shared__ int s_last;
 
@@ -314,6 +330,68 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
         nbox[j] = (i0 >= 0) ? __ldg(boxb + i0) : make_uint2(0xffff7fffu, 0xffff7fffu);
     }
 #endif
+#if GGS_DENSE_STAGE
+    // A round only compacts the INDICES of the splats that touch the tile (ordered, by ballot and
+    // a cross-warp prefix); the records are staged when the list is about to be composited, one
+    // list entry per thread, so the staging code runs ceil(cnt / kThreads) times per flush instead
+    // of once per (round, slot) with a few lanes active.
+    int par = 0;
+    for (int top = N; top > 0; top -= kScanChunk) {
+        bool hit[kScanPerThread];
+        unsigned bal[kScanPerThread];
+#pragma unroll
+        for (int j = 0; j < kScanPerThread; ++j) {
+            const uint2 box = nbox[j];
+            const int bx0 = (int)(short)(box.x & 0xffff), bx1 = (int)box.x >> 16;
+            const int by0 = (int)(short)(box.y & 0xffff), by1 = (int)box.y >> 16;
+            hit[j] = (bx1 >= X0) & (bx0 <= X1) & (by1 >= Y0) & (by0 <= Y1);
+            bal[j] = __ballot_sync(0xffffffffu, hit[j]);
+            if (lane == 0) s_wcnt[par][j][warp] = __popc(bal[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < kScanPerThread; ++j) {
+            const int i1 = top - kScanChunk - 1 - (j * kThreads + tid);
+            nbox[j] = (i1 >= 0) ? __ldg(boxb + i1) : make_uint2(0xffff7fffu, 0xffff7fffu);
+        }
+        __syncthreads();
+        int run = cnt;
+#pragma unroll
+        for (int j = 0; j < kScanPerThread; ++j) {
+            int pre = 0, tot = 0;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const int c = s_wcnt[par][j][w];
+                pre += (w < warp) ? c : 0;
+                tot += c;
+            }
+            if (hit[j]) s_idx[run + pre + __popc(bal[j] & (lanebit - 1u))] = top - 1 - (j * kThreads + tid);
+            run += tot;
+        }
+        cnt = run;
+        par ^= 1;  // the next round's counts go to the other buffer: one barrier per round
+        if (cnt > kListCap - kScanChunk || top <= kScanChunk) {
+            __syncthreads();
+            for (int e = tid; e < cnt; e += kThreads) {
+                const int i = s_idx[e];
+                const uint2 box = __ldg(boxb + i);
+                const float4 *src = recb + (int64_t)i * 3;
+                float4 q2 = __ldg(src + 2);
+                q2.y = __uint_as_float(lane_mask((int)(short)(box.x & 0xffff), (int)box.x >> 16, X0));
+                q2.z = __uint_as_float(row_code((int)(short)(box.y & 0xffff), (int)box.y >> 16, Y0,
+                                                q2.w < 0.0f));
+                cp_async16(&s_list[e * 3 + 0], src + 0);  // LDGSTS: no register staging
+                cp_async16(&s_list[e * 3 + 1], src + 1);
+                s_list[e * 3 + 2] = q2;
+            }
+            cp_async_wait_all();
+            __syncthreads();
+            if (live) live = composite_list<kStats>(s_list, cnt, lanebit, band_sel, Xf, Ybf, work);
+            cnt = 0;
+            // every band opaque: the rest of the genome is hidden behind what is drawn
+            if (__syncthreads_and(!live)) break;
+        }
+    }
+#else
     for (int top = N; top > 0; top -= kScanChunk) {
         bool hit[kScanPerThread];
         unsigned bal[kScanPerThread];
@@ -363,7 +441,7 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
                 const float4 *src = recb + (int64_t)idx[j] * 3;
                 float4 q2 = __ldg(src + 2);
                 q2.y = __uint_as_float(lane_mask(bx0[j], bx1[j], X0));
-                q2.z = __uint_as_float(row_code(by0[j], by1[j], Y0));
+                q2.z = __uint_as_float(row_code(by0[j], by1[j], Y0, q2.w < 0.0f));
                 cp_async16(&s_list[pos * 3 + 0], src + 0);  // LDGSTS: no register staging
                 cp_async16(&s_list[pos * 3 + 1], src + 1);
                 s_list[pos * 3 + 2] = q2;
@@ -380,6 +458,8 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
             if (__syncthreads_and(!live)) break;
         }
     }
+
+#endif
 
     // Epilogue: add the background through the remaining transmittance (render.py:236-237),
     // clamp (render.py:252), optional image store, squared error (fitness.py:16-31).
