@@ -320,13 +320,17 @@ int ggs_ctx_create(int device, ggs_ctx **out)
         return GGS_EINVAL;
     }
     c->device = device;
-    GGS_CUDA(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-        GGS_CUDA(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
-        GGS_CUDA(cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming));
+    cudaError_t e = cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
     }
-    for (int i = 0; i < kMaxSlices; ++i)
-        GGS_CUDA(cudaEventCreateWithFlags(&c->landed[i], cudaEventDisableTiming));
+    for (int i = 0; i < kMaxSlices && e == cudaSuccess; ++i)
+        e = cudaEventCreateWithFlags(&c->landed[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        ggs_ctx_destroy(c);  // releases whatever was created
+        return cuda_fail(e, "ggs_ctx_create: stream / event creation");
+    }
     *out = c;
     return GGS_OK;
 }

@@ -138,6 +138,8 @@ CASES = [
     (3, 1000, 256, 256, 44, False),    # config 3 shape, 3 candidates
     (2, 700, 200, 136, 45, True),      # ragged, late-run distribution
     (1, 1500, 64, 96, 46, False),      # many splats per tile: several list flushes
+    (2, 4000, 512, 512, 47, False),    # config 4 shape: bands saturate, hidden splats skipped
+    (1, 2000, 1024, 1024, 48, True),   # sweep corner: 1,024 tiles per candidate
 ]
 
 
