@@ -465,6 +465,27 @@ def test_uint8_frames_match_the_reference_conversion(ggs, golden):
     assert np.abs(frame.astype(np.int16) - ref8[0]).max() <= 1
 
 
+def one_ulp_sensitivity(g, t, H, W, k, bg):
+    """How far the ORACLE's own image (max abs) and plain fitness (relative) move, per candidate,
+    when one group of genes -- centre, log-sigmas, angle -- moves by one ulp up or down.  inf
+    where a probe turns non-finite."""
+    B = g.shape[0]
+    img0 = oracle.render(oracle.encode(g), H, W, k, background=bg)
+    fit0 = oracle.fitness(g, t, H, W, k).astype(np.float64)
+    img_d, fit_d = np.zeros(B), np.zeros(B)
+    for cols in (slice(0, 2), slice(2, 4), slice(4, 5)):
+        for toward in (np.inf, -np.inf):
+            n = g.copy()
+            n[..., cols] = np.nextafter(n[..., cols], np.float32(toward))
+            with np.errstate(invalid="ignore", divide="ignore"):
+                d = np.abs(oracle.render(oracle.encode(n), H, W, k, background=bg) - img0)
+                f = np.abs(oracle.fitness(n, t, H, W, k).astype(np.float64) / fit0 - 1.0)
+            d = d.reshape(B, -1).max(axis=1, initial=0.0)
+            img_d = np.maximum(img_d, np.where(np.isfinite(d), d, np.inf))
+            fit_d = np.maximum(fit_d, np.where(np.isfinite(f), f, np.inf))
+    return img_d, fit_d
+
+
 def test_randomised_shapes_against_oracle(ggs):
     """Seeded fuzz over image sizes, splat counts, k_sigma, layouts, backgrounds and modes."""
     from ggs_b200 import synth
@@ -500,27 +521,34 @@ def test_randomised_shapes_against_oracle(ggs):
         #  * short of that, the image depends on the last bit of exp(log sigma): moving the two
         #    log-sigma genes by ONE ulp moves the reference's own image by more than the
         #    tolerance (the reference under the Triton interpreter, torch.exp on the CPU, and the
-        #    reference on a GPU, CUDA expf, differ by exactly such bits).
-        # Such candidates have no result to be on a par with.  Only a candidate that misses the
-        # tolerance is tested for this, and it must show the sensitivity to be excused.
+        #    reference on a GPU, CUDA expf, differ by exactly such bits); when the variances sit
+        #    on the reference's 1e-6 floor (conic entries of 1e12) the same holds for one ulp of
+        #    the centre instead: the quadratic is then rounding noise of magnitude 1e8.
+        # Such candidates have no result to be on a par with.  Only a candidate that misses a
+        # tolerance is tested for this (one_ulp_sensitivity), and it must show the sensitivity --
+        # in the image for an image miss, in the fitness for a fitness miss -- to be excused.
         with np.errstate(invalid="ignore"):
             err = np.abs(img - img_ref).reshape(B, -1).max(axis=1, initial=0.0)
         defined = np.isfinite(img_ref).reshape(B, -1).all(axis=1) & (err <= IMG_TOL)
+        sens = None   # the oracle's own one-ulp sensitivity, computed only if something misses
         if not defined.all():
-            nudged = chol.copy()
-            nudged[..., 2:4] = np.nextafter(nudged[..., 2:4], np.float32(np.inf))
-            with np.errstate(invalid="ignore"):
-                drift = np.abs(oracle.render(nudged, H, W, k, background=bg) - img_ref)
-            drift = drift.reshape(B, -1).max(axis=1, initial=0.0)
-            excused = ~np.isfinite(drift) | (drift > 0.5 * IMG_TOL)
-            assert (defined | excused).all(), (trial, H, W, N, B, k, err, drift)
-        n_undefined += int((~defined).sum())
+            sens = one_ulp_sensitivity(g, t, H, W, k, bg)
+            excused = sens[0] > 0.5 * IMG_TOL
+            assert (defined | excused).all(), (trial, H, W, N, B, k, err, sens[0])
         for kw in ({}, {"weight_mask": m}, {"weight_mask": m, "boost_only": True}):
             f_ref = oracle.fitness(g, t, H, W, k, **kw)
             kw_gpu = {a: (cuda(v) if isinstance(v, np.ndarray) else v) for a, v in kw.items()}
             f = ggs.fitness(cuda(g), cuda(t), H, W, k, **kw_gpu).cpu().numpy()
-            np.testing.assert_allclose(f[defined], f_ref[defined], rtol=FIT_RTOL,
-                                       err_msg=str((trial, H, W, N, B, k, list(kw))))
+            with np.errstate(invalid="ignore"):
+                off = defined & ~(np.abs(f - f_ref) <= FIT_RTOL * np.abs(f_ref))
+            if off.any():
+                # image inside 1e-4 everywhere, fitness outside 1e-5: excused only if the
+                # reference's own fitness moves that much under a one-ulp change of a gene
+                sens = sens if sens is not None else one_ulp_sensitivity(g, t, H, W, k, bg)
+                assert (~off | (sens[1] > 0.5 * FIT_RTOL)).all(), \
+                    (trial, H, W, N, B, k, list(kw), f, f_ref, sens[1])
+                defined = defined & ~off
+        n_undefined += int((~defined).sum())
     print(f"AABB flips over the fuzz set: {n_flips}; candidates undefined in the reference: {n_undefined}")
     assert n_flips <= max(2, trials // 50)
     assert n_undefined <= max(1, trials // 20)
