@@ -33,8 +33,9 @@ d = np.abs(out - ref).max(axis=-1)
 print("max diff", d.max(), "candidates", d.reshape(B, -1).max(axis=1))
 b, y, x = np.unravel_index(np.argmax(d), d.shape)
 print("worst pixel b,y,x", b, y, x, "ref", ref[b, y, x], "gpu", out[b, y, x])
-ys, xs = np.nonzero(d[b] > 1e-4)
-print("pixels over 1e-4:", len(ys), "y", ys.min(), ys.max(), "x", xs.min(), xs.max())
+thr = 1e-4 if d.max() > 1e-4 else 0.5 * float(d.max())
+ys, xs = np.nonzero(d[b] > thr)
+print(f"pixels over {thr:.1e}:", len(ys), "y", ys.min(), ys.max(), "x", xs.min(), xs.max())
 # which splat: render each splat of candidate b alone
 dec = oracle.decode(chol, H, W, k)
 worst = []
