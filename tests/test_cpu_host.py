@@ -30,6 +30,38 @@ def test_library_exports_every_declared_symbol():
     assert L.ggs_abi_version() == native.ABI_VERSION
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Argument counts and the obvious argument kinds of native.SIGNATURES follow the prototypes
+    in include/ggs_b200.h (a drifted binding would corrupt the call without any GPU to notice)."""
+    from ggs_b200 import native
+    text = open(os.path.join(ROOT, "include", "ggs_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    protos = re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(ggs_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text)
+    assert len(protos) >= 30
+    ctype_of = {"int": ctypes.c_int, "int64_t": ctypes.c_int64, "float": ctypes.c_float,
+                "double": ctypes.c_double, "size_t": ctypes.c_size_t, "uint64_t": ctypes.c_uint64,
+                "uint32_t": ctypes.c_uint32}
+    for ret, name, params in protos:
+        res, args = native.SIGNATURES[name]
+        plist = [] if params.strip() in ("", "void") else [q.strip() for q in params.split(",")]
+        assert len(plist) == len(args), f"{name}: header has {len(plist)} parameters, binding {len(args)}"
+        for q, a in zip(plist, args):
+            if "*" in q:    # any pointer: void_p or a typed POINTER
+                assert a is ctypes.c_void_p or a is ctypes.c_char_p or hasattr(a, "_type_") and \
+                    issubclass(a, ctypes._Pointer), f"{name}: `{q}` bound as {a}"
+            else:
+                want = q.replace("const ", "").split()[0]
+                assert a is ctype_of[want], f"{name}: `{q}` bound as {a}"
+        ret = ret.replace("const", "").strip()
+        if "*" in ret:
+            assert res in (ctypes.c_char_p, ctypes.c_void_p)
+        elif ret == "void":
+            assert res is None
+        else:
+            assert res is ctype_of[ret], f"{name}: returns {ret}, bound as {res}"
+
+
 def test_workspace_size_is_monotone_and_nonzero():
     import ggs_b200
     L = ggs_b200.lib()
