@@ -62,14 +62,16 @@ def synthetic_target_np(H: int, W: int, seed: int = 0) -> np.ndarray:
 
 
 def importance_mask_np(target: np.ndarray, strength: float = 0.7) -> np.ndarray:
-    """The mask the GA loop builds (algorithm.py:42-49) for a synthetic target."""
+    """The mask the GA loop builds (algorithm.py:42-49) for a synthetic target, computed by the
+    library on the current CUDA device (ggs_importance_mask; there is no CPU path -- CPU-only
+    tests use the torch restatement in oracle/torch_ref.py)."""
     import torch
-    from modules.mask import compute_importance_mask
+    from .evaluator import importance_mask
     H, W = target.shape[:2]
-    m = compute_importance_mask(torch.from_numpy(target), H, W, edge_scales=(1, 2, 4),
-                                w_edge=0.7, w_var=0.3, gamma=0.7, floor=0.15, smooth=3,
-                                strength=strength)
-    return np.ascontiguousarray(m.numpy().astype(np.float32))
+    m = importance_mask(torch.from_numpy(np.ascontiguousarray(target, dtype=np.float32)).cuda(), H, W,
+                        edge_scales=(1, 2, 4), w_edge=0.7, w_var=0.3, gamma=0.7, floor=0.15,
+                        smooth=3, strength=strength)
+    return np.ascontiguousarray(m.cpu().numpy().astype(np.float32))
 
 
 def count_pairs(x0, x1, y0, y1) -> int:

@@ -25,7 +25,6 @@ except Exception:
 
 from modules.algorithm import prepare_target
 from modules.fitness import fitness_many
-from modules.genetic import mutate_population
 from modules.mask import compute_importance_mask
 from modules.population import new_individual
 from ggs_b200 import breed
@@ -187,17 +186,15 @@ def simulated_annealing(
     def propose(state: torch.Tensor, count: int, it: int) -> torch.Tensor:
         """`count` independently mutated copies of `state` (annealing.py:121-128, batched)."""
         nb = state.unsqueeze(0).repeat(count, 1, 1)
-        if nb.is_cuda:
-            # one launch: the GA breeding kernel with identical parents and no crossover is
-            # exactly `count` independent mutate_individual calls
-            draws[0] += 1
-            sigma = build_mut_sigma(it, iterations, sigma_schedule, mut_sigma_max, mut_sigma_min)
-            lo, hi = scale_log_bounds(H, W, min_scale_splats, max_scale_splats)
-            return breed(nb, torch.zeros(count, device=nb.device), sigma, tour_k=1, cxpb=0.0,
-                         mutpb=mutpb, log_scale_lo=lo, log_scale_hi=hi, seed=run_seed,
-                         generation=draws[0])
-        return mutate_population(nb, it, iterations, sigma_schedule, mut_sigma_max, mut_sigma_min,
-                                 mutpb, H, W, min_scale_splats, max_scale_splats)
+        assert nb.is_cuda, "simulated_annealing needs a CUDA device (no CPU path)"
+        # one launch: the GA breeding kernel with identical parents and no crossover is
+        # exactly `count` independent mutate_individual calls
+        draws[0] += 1
+        sigma = build_mut_sigma(it, iterations, sigma_schedule, mut_sigma_max, mut_sigma_min)
+        lo, hi = scale_log_bounds(H, W, min_scale_splats, max_scale_splats)
+        return breed(nb, torch.zeros(count, device=nb.device), sigma, tour_k=1, cxpb=0.0,
+                     mutpb=mutpb, log_scale_lo=lo, log_scale_hi=hi, seed=run_seed,
+                     generation=draws[0])
 
     curr = new_individual(n_splats, H, W, min_scale_splats, max_scale_splats, device=device)
     tries = max(1, tries_per_iter)

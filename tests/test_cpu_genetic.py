@@ -1,4 +1,6 @@
-"""CPU tests of the host-side callers of the hot path (modules/genetic.py, utils.py, ...)."""
+"""CPU tests of the host-side callers of the hot path (modules/utils.py, population.py, ...) and of
+the torch restatement of the GA operators (oracle/torch_ref.py) that the CUDA breeding kernel is
+checked against."""
 import math
 
 import numpy as np
@@ -6,6 +8,7 @@ import torch
 
 import modules.config as C
 from modules import genetic as G
+from oracle import torch_ref as T
 from modules import population as P
 from modules import resize as R
 from modules import utils as U
@@ -52,18 +55,13 @@ def test_mutation_keeps_genomes_legal_and_touches_every_group():
     torch.manual_seed(1)
     pop = P.new_population(16, 50, 64, 96, 3.0, 0.1, device="cpu")
     before = pop.clone()
-    G.mutate_population(pop, 3, 100, "cosine", C.MUT_SIGMA_MAX, C.MUT_SIGMA_MIN, 0.0, 64, 96, 3.0, 0.1)
+    T.mutate_population(pop, 3, 100, "cosine", C.MUT_SIGMA_MAX, C.MUT_SIGMA_MIN, 0.0, 64, 96, 3.0, 0.1)
     lo, hi = U.scale_log_bounds(64, 96, 3.0, 0.1)
     assert pop[..., :2].min() >= 0 and pop[..., :2].max() <= 1
     assert pop[..., 2:4].min() >= lo - 1e-6 and pop[..., 2:4].max() <= hi + 1e-6
     assert pop[..., 5:9].min() >= 0 and pop[..., 5:9].max() <= 255
     # mutpb = 0: only the "at least one" genes and the swap change, yet every individual changes
     assert ((pop != before).reshape(16, -1).sum(1) > 0).all()
-    # the multiset of splats is preserved up to the few mutated genes: a swap moves rows intact
-    ind = pop[0].clone()
-    out = G.mutate_individual(ind, False, 3, 100, "cosine", C.MUT_SIGMA_MAX, C.MUT_SIGMA_MIN, 0.05,
-                              64, 96, 3.0, 0.1)
-    assert out is ind
 
 
 def test_swap_brings_a_bigger_splat_forward():
@@ -71,7 +69,7 @@ def test_swap_brings_a_bigger_splat_forward():
     N = 30
     pop = P.new_population(64, N, 64, 64, 3.0, 0.1, device="cpu")
     size0 = (pop[..., 2] + pop[..., 3]).exp()
-    G.mutate_population(pop, 100, 100, "cosine", {k: 0.0 for k in C.MUT_SIGMA_MAX},
+    T.mutate_population(pop, 100, 100, "cosine", {k: 0.0 for k in C.MUT_SIGMA_MAX},
                         {k: 0.0 for k in C.MUT_SIGMA_MIN}, 0.0, 64, 64, 3.0, 0.1)
     size1 = (pop[..., 2] + pop[..., 3]).exp()
     moved = (size0 - size1).abs() > 1e-6
@@ -87,13 +85,13 @@ def test_swap_brings_a_bigger_splat_forward():
 def test_tournament_and_crossover():
     torch.manual_seed(5)
     fit = torch.arange(100, dtype=torch.float32)
-    idx = G.tournament_indices(fit, 4000, k=2)
+    idx = T.tournament_indices(fit, 4000, k=2)
     assert idx.min() >= 0 and idx.max() < 100
     assert idx.float().mean() < 40        # E[min of two uniform draws] ~ 33 < 49.5
     parents = torch.arange(6 * 4 * 9, dtype=torch.float32).reshape(6, 4, 9)
-    same = G.crossover_population(parents, cxpb=0.0)
+    same = T.crossover_population(parents, cxpb=0.0)
     assert torch.equal(same, parents)
-    mixed = G.crossover_population(parents, cxpb=1.0)
+    mixed = T.crossover_population(parents, cxpb=1.0)
     for k in range(3):       # rows are exchanged whole, pair-wise: the pair's multiset is kept
         pair_in = torch.cat([parents[2 * k], parents[2 * k + 1]]).sort(0).values
         pair_out = torch.cat([mixed[2 * k], mixed[2 * k + 1]]).sort(0).values
@@ -113,16 +111,40 @@ def test_temperature_schedule():
     assert _temp_schedule("cauchy", 1.0, 9, 100) == 0.1
 
 
-def test_breed_population_cpu_path_keeps_shape_and_box():
-    # on CPU tensors breed_population composes the batched torch operators (the CUDA launch
-    # needs a device); same contract: [P,N,9] legal genomes
+def test_breed_population_torch_reference_keeps_shape_and_box():
+    # the torch composition the CUDA breeding kernel is compared with: [P,N,9] legal genomes
     torch.manual_seed(2)
     pop = P.new_population(10, 30, 64, 64, 3.0, 0.1, device="cpu")
     fit = torch.rand(10)
-    off = G.breed_population(pop, fit, 3, 50, "cosine", C.MUT_SIGMA_MAX, C.MUT_SIGMA_MIN, 2, 0.5,
-                             0.05, 64, 64, 3.0, 0.1)
+    off = T.breed_population_torch(pop, fit, 3, 50, "cosine", C.MUT_SIGMA_MAX, C.MUT_SIGMA_MIN, 2,
+                                   0.5, 0.05, 64, 64, 3.0, 0.1)
     lo, hi = U.scale_log_bounds(64, 64, 3.0, 0.1)
     assert off.shape == (10, 30, 9) and off.data_ptr() != pop.data_ptr()
     assert off[..., :2].min() >= 0 and off[..., :2].max() <= 1
     assert off[..., 2:4].min() >= lo - 1e-6 and off[..., 2:4].max() <= hi + 1e-6
     assert off[..., 5:9].min() >= 0 and off[..., 5:9].max() <= 255
+
+
+def test_product_operators_have_no_cpu_path():
+    # modules/genetic.py and modules/mask.py are device-only: a CPU box fails loudly
+    import pytest
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    pop = P.new_population(4, 6, 32, 32, 3.0, 0.1, device="cpu")
+    with pytest.raises(AssertionError):
+        G.breed_population(pop, torch.rand(4), 1, 10, "cosine", C.MUT_SIGMA_MAX, C.MUT_SIGMA_MIN, 2,
+                           0.5, 0.05, 32, 32, 3.0, 0.1)
+    with pytest.raises(AssertionError):
+        G.mutate_individual(pop[0], False, 1, 10, "cosine", C.MUT_SIGMA_MAX, C.MUT_SIGMA_MIN, 0.05,
+                            32, 32, 3.0, 0.1)
+    from modules.mask import compute_importance_mask
+    with pytest.raises(AssertionError):
+        compute_importance_mask(torch.rand(16, 16, 3), 16, 16)
+
+
+def test_schedules_agree_with_the_torch_reference():
+    for kind in ("cosine", "linear", "exp", "other"):
+        for g in (0, 1, 37, 100, 150):
+            assert abs(U._anneal_factor(g, 100, kind) - T.anneal_factor(g, 100, kind)) < 1e-15
+    assert U.build_mut_sigma(30, 100, "cosine", C.MUT_SIGMA_MAX, C.MUT_SIGMA_MIN) == \
+        T.build_mut_sigma(30, 100, "cosine", C.MUT_SIGMA_MAX, C.MUT_SIGMA_MIN)

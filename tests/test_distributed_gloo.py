@@ -32,12 +32,12 @@ def _worker(rank, world, port, P, q):
     try:
         from ggs_b200 import synth
         from ggs_b200.distributed import ShardedEvaluator, shard_bounds
-        from oracle import oracle
+        from oracle import oracle, torch_ref
         oracle.set_threads(1)
         N, H, W = 12, 24, 40
         g = torch.from_numpy(synth.new_population_np(P, N, H, W, seed=3))
         t = synth.synthetic_target_np(H, W, 3)
-        m = synth.importance_mask_np(t)
+        m = torch_ref.importance_mask_np(t)
 
         def evaluate(x):
             return torch.from_numpy(oracle.fitness(x.numpy(), t, H, W, 3.0, weight_mask=m))

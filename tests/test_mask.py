@@ -30,8 +30,8 @@ IDS = [c[0] for c in CASES]
 
 @pytest.mark.parametrize("name,image,H,W,kw,want", CASES, ids=IDS)
 def test_torch_path_matches_reference_goldens(name, image, H, W, kw, want):
-    from modules.mask import compute_importance_mask
-    got = compute_importance_mask(torch.from_numpy(image), H, W, **kw)
+    from oracle.torch_ref import importance_mask_torch
+    got = importance_mask_torch(torch.from_numpy(image), H, W, **kw)
     assert got.shape == (H, W) and got.dtype == torch.float32
     assert np.abs(got.numpy() - want).max() <= 1e-6
 
@@ -76,12 +76,16 @@ def test_cuda_mask_matches_goldens_of_the_render_cases(golden):
 def test_cuda_mask_matches_torch_path_at_config_sizes(H0, W0, H, W):
     from ggs_b200 import synth
     from modules.mask import compute_importance_mask
+    from oracle.torch_ref import importance_mask_torch
     image = torch.from_numpy(synth.synthetic_target_np(H0, W0, 3))
     kw = dict(edge_scales=(1, 2, 4), w_edge=0.7, w_var=0.3, gamma=0.7, floor=0.15, smooth=3,
               strength=0.7)
-    want = compute_importance_mask(image, H, W, **kw)
+    want = importance_mask_torch(image, H, W, **kw)
     got = compute_importance_mask(image.cuda(), H, W, **kw)
     assert np.abs(got.cpu().numpy() - want.numpy()).max() <= MASK_TOL
+    # a host tensor goes through the same kernels and comes back on the host (no CPU path)
+    back = compute_importance_mask(image, H, W, **kw)
+    assert not back.is_cuda and torch.equal(back, got.cpu())
     # and the masked fitness that results is the same to the fitness tolerance
     import ggs_b200
     g = torch.from_numpy(synth.new_population_np(4, 60, H, W, seed=8)).cuda()
@@ -96,9 +100,9 @@ def test_cuda_mask_degenerate_inputs():
     import ggs_b200
     # a constant image: every cue is flat, quantiles coincide, (t - ql) / 1e-12 clamps to 0
     flat = torch.full((40, 56, 3), 0.25).cuda()
-    from modules.mask import compute_importance_mask
+    from oracle.torch_ref import importance_mask_torch
     kw = dict(edge_scales=(1, 2, 4), smooth=3, strength=0.7)
-    want = compute_importance_mask(flat.cpu(), 40, 56, **kw)
+    want = importance_mask_torch(flat.cpu(), 40, 56, **kw)
     got = ggs_b200.importance_mask(flat, 40, 56, **kw)
     assert np.abs(got.cpu().numpy() - want.numpy()).max() <= MASK_TOL
     # 1x1 work size, scale 1 only
@@ -118,7 +122,7 @@ def test_cuda_mask_quantiles_are_exact_order_statistics():
     import ggs_b200
     # Feed a plane through the public entry with parameters that reduce the pipeline to
     # norm01(norm01-mix): compare against the torch path on awkward value distributions.
-    from modules.mask import compute_importance_mask
+    from oracle.torch_ref import importance_mask_torch
     rng = np.random.default_rng(5)
     for trial in range(6):
         H, W = int(rng.integers(3, 90)), int(rng.integers(3, 90))
@@ -128,6 +132,6 @@ def test_cuda_mask_quantiles_are_exact_order_statistics():
             img = np.clip(img, 0, 1)
         kw = dict(edge_scales=(1, 2), w_edge=0.6, w_var=0.4, gamma=0.9, floor=0.1, smooth=0,
                   strength=1.0)
-        want = compute_importance_mask(torch.from_numpy(img), H, W, **kw)
+        want = importance_mask_torch(torch.from_numpy(img), H, W, **kw)
         got = ggs_b200.importance_mask(torch.from_numpy(img).cuda(), H, W, **kw)
         assert np.abs(got.cpu().numpy() - want.numpy()).max() <= MASK_TOL, (trial, H, W)

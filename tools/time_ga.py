@@ -7,7 +7,8 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "genetic-gaussian-splats_b200")]
 import torch
 import modules.config as C
 from modules.fitness import fitness_many
-from modules.genetic import breed_population, crossover_population, mutate_population, tournament_indices
+from modules.genetic import breed_population
+from oracle.torch_ref import crossover_population, mutate_population, tournament_indices
 from modules.population import new_population
 from ggs_b200 import synth
 
