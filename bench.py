@@ -80,27 +80,112 @@ def ncu_traffic(workload: str, population: int):
     return best
 
 
-def reference_gpu_recorded(workload: str):
-    """The reference's real Triton path on a B200, as RECORDED by tools/reference_gpu_compare.py
-    (profiles/rNN_reference_gpu_compare.json): it cannot run inside bench.py (the reference is
-    not on the GPU box).  Context for the reader, not a live measurement."""
-    tag = {"c1": "config 1", "c2": "config 2", "c3": "config 3"}.get(workload)
-    pdir = os.path.join(ROOT, "profiles")
-    found = None
-    for name in sorted(os.listdir(pdir)) if (tag and os.path.isdir(pdir)) else []:
-        if name.endswith("_reference_gpu_compare.json"):
-            try:
-                rec = json.load(open(os.path.join(pdir, name)))
-            except Exception:
-                continue
-            for row in rec.get("rows", []):
-                if row.get("shape", "").startswith(tag):
-                    found = {"value": row["reference_candidates_per_s"], "unit": UNIT,
-                             "ms_per_call": row["reference_ms_per_call"],
-                             "candidates_per_call": row["candidates"], "source": "profiles/" + name,
-                             "what": "unmodified reference (Triton) through fitness_population on "
-                                     "one B200, recorded run, wall clock"}
-    return found
+def workload_config(wl, gpus: int) -> dict:
+    """The `config` object of the JSON line: a function of the workload and the GPU count only,
+    so both arms (`--impl ours` / `--impl reference`) print the same one."""
+    P, N = wl["P"], wl["N"]
+    pool_bytes = POOL * P * N * 9 * 4
+    return {"workload": wl["desc"], "H": wl["H"], "W": wl["W"], "splats": N,
+            "population_per_gpu": P, "population_total": gpus * P,
+            "fitness": "mask" if wl["mask"] else "plain", "k_sigma": 3.0,
+            "parallelism": (f"population sharded over {gpus} GPU(s), fitness vector gathered on "
+                            f"every rank") if gpus > 1 else "1 GPU",
+            "l2": (f"inputs rotate over {POOL} populations ({pool_bytes / 1e6:.0f} MB > 126 MB L2)"
+                   if pool_bytes > 126e6 else
+                   f"inputs rotate over {POOL} populations ({pool_bytes / 1e6:.0f} MB); "
+                   f"compute-bound, {N * 36} B of genome per candidate")}
+
+
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def reference_gpu_available() -> bool:
+    return os.path.isdir(os.path.join(REF_DIR, "modules"))
+
+
+def reference_gpu_live(args, wl, device_index: int, budget_s: float = 25.0):
+    """The UNMODIFIED reference (baseline/_ref, git-ignored copy of /root/reference) through its
+    stock path -- prewarm_renderer, then fitness_population -> fitness_many ->
+    render_splats_rgb_triton (its Triton kernel, JIT-compiled for this GPU) -- on the same
+    genomes, target and workload, timed live in a child process (both trees call their package
+    `modules`).  Returns (dict for the JSON line, path of an .npz with its mask and fitness)."""
+    if not reference_gpu_available():
+        return {"unavailable": "baseline/_ref missing (run baseline/make_ref_copy.sh in the build "
+                               "container; /root/reference does not exist on the GPU box)"}, None
+    import tempfile
+    out_npz = os.path.join(tempfile.mkdtemp(prefix="ggs_ref_"), "ref.npz")
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference-gpu-child",
+           "--workload", args.workload, "--population", str(wl["P"]), "--side", str(wl["H"]),
+           "--splats", str(wl["N"]), "--ref-out", out_npz, "--ref-budget", str(budget_s)]
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "")
+               .split(",")[device_index] if os.environ.get("CUDA_VISIBLE_DEVICES") else str(device_index))
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=420, env=env)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not line:
+            return {"unavailable": "reference child failed: " + (r.stderr.strip().splitlines() or ["?"])[-1][:300]}, None
+        return json.loads(line[-1]), out_npz
+    except Exception as e:  # timeout, ...
+        return {"unavailable": f"reference child: {type(e).__name__}: {e}"[:300]}, None
+
+
+def run_reference_gpu_child(args, wl):
+    """Child process of reference_gpu_live: nothing of this repository's product is imported."""
+    import importlib.util
+    sys.path[:] = [p for p in sys.path if os.path.abspath(p or ".") not in (ROOT, PKG)]
+    sys.path.insert(0, REF_DIR)
+    import torch
+    import modules.fitness as rfit
+    import modules.mask as rmask
+    import modules.utils as rutils
+    assert os.path.abspath(rfit.__file__).startswith(REF_DIR), rfit.__file__
+    spec = importlib.util.spec_from_file_location("ggs_synth", os.path.join(PKG, "ggs_b200", "synth.py"))
+    synth = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(synth)           # numpy only: seeded inputs, not product code
+    H, W, N, P = wl["H"], wl["W"], wl["N"], wl["P"]
+    t_np = synth.synthetic_target_np(H, W, 0)
+    target = torch.from_numpy(t_np).cuda()
+    mask = None
+    if wl["mask"]:                           # algorithm.py:42-49
+        mask = rmask.compute_importance_mask(target, H, W, edge_scales=(1, 2, 4), w_edge=0.7,
+                                             w_var=0.3, gamma=0.7, floor=0.15, smooth=3,
+                                             strength=0.7).to("cuda")
+    pop = list(torch.from_numpy(synth.new_population_np(P, N, H, W, seed=42)).cuda().unbind(0))
+    rutils.prewarm_renderer(H, W, 3.0, "cuda")      # algorithm.py:52
+
+    def call():
+        return rfit.fitness_population(pop, target, H, W, 3.0, "cuda", tile=32, chunk=None,
+                                       weight_mask=mask, boost_only=False)
+    fit = call()                              # warm-up: Triton JIT for this shape
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    fit = call()
+    torch.cuda.synchronize()
+    first = time.perf_counter() - t0
+    reps = int(max(1, min(20, args.ref_budget / max(first, 1e-4))))
+    times = [first]
+    for _ in range(reps - 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        fit = call()
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    if args.ref_out:
+        np.savez(args.ref_out, fitness=np.asarray(fit, dtype=np.float64),
+                 mask=(mask.cpu().numpy() if mask is not None else np.zeros(0, np.float32)))
+    import triton
+    best, mean = min(times), sum(times) / len(times)
+    emit({"value": P / mean, "unit": UNIT, "candidates": P, "ms_per_call": mean * 1e3,
+          "best_ms_per_call": best * 1e3, "calls_timed": len(times),
+          "what": "unmodified reference (baseline/_ref = /root/reference/modules) through "
+                  "prewarm_renderer + fitness_population(list) -> List[float] "
+                  "(fitness.py:35-48 -> render_splats_rgb_triton, Triton JIT), same GPU, same "
+                  "genomes / target, wall clock around synchronised calls after one warm-up call",
+          "triton": triton.__version__, "torch": torch.__version__,
+          "gpu": torch.cuda.get_device_name(0)})
+    return 0
 
 
 def dist_env():
@@ -181,15 +266,25 @@ class ClockSampler:
 
 # ------------------------------------------------------------------ CPU (reference) arm
 
+def host_cores() -> int:
+    """Host threads this process may use (its affinity mask, else the CPU count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample(wl, seconds: float, rank_seed: int = 0):
     """Times the CPU oracle (the restatement of the reference's arithmetic; the reference has
     no CPU path of its own) on a bounded sample of the workload.  Returns (cands/s, sample)."""
     from ggs_b200 import synth
     from oracle import oracle
+    from oracle import torch_ref
     H, W, N = wl["H"], wl["W"], wl["N"]
-    cores = oracle.threads()
+    cores = host_cores()
+    oracle.set_threads(cores)    # explicit: torchrun exports OMP_NUM_THREADS=1
     t = synth.synthetic_target_np(H, W, 0)
-    m = synth.importance_mask_np(t) if wl["mask"] else None
+    m = torch_ref.importance_mask_np(t) if wl["mask"] else None
     probe = synth.new_population_np(cores, N, H, W, seed=42 + rank_seed)
     t0 = time.perf_counter()
     oracle.fitness(probe, t, H, W, 3.0, weight_mask=m)
@@ -203,12 +298,17 @@ def cpu_sample(wl, seconds: float, rank_seed: int = 0):
 
 
 def run_reference(args, wl):
-    rank, _, world = dist_env()
+    """The reference arm.  The reference has no CPU implementation of this path (render.py:217
+    asserts CUDA), so `value` is the CPU restatement of its arithmetic (oracle/ggs_oracle.c) on
+    all host cores, as the task's tier rules ask; next to it, `reference_gpu` is the reference's
+    REAL path -- its Triton kernel on this GPU -- timed live when baseline/_ref travelled here."""
+    rank, local_rank, world = dist_env()
     if rank != 0:
         return 0
     from oracle import oracle
     oracle.build()
-    cores = oracle.threads()
+    cores = host_cores()
+    oracle.set_threads(cores)
     per_step = max(0.5, min(20.0, 120.0 / max(1, args.steps + args.warmup)))  # ~2 min in all
     for _ in range(args.warmup):
         cpu_sample(wl, per_step / 4)
@@ -220,19 +320,27 @@ def run_reference(args, wl):
         t_total += dt
     value = float(np.mean(vals))
     sample = (f"{n_last} candidates of {wl['H']}x{wl['W']}/{wl['N']} splats per step, "
-              f"CPU oracle (oracle/ggs_oracle.c, OpenMP over candidates)")
+              f"CPU oracle (oracle/ggs_oracle.c, OpenMP over candidates, {cores} threads)")
+    ref_gpu = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            ref_gpu, _ = reference_gpu_live(args, wl, local_rank)
+    except Exception as e:
+        ref_gpu = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "H": wl["H"], "W": wl["W"], "splats": wl["N"],
-                   "population_per_gpu": wl["P"], "fitness": "mask" if wl["mask"] else "plain",
-                   "note": "the reference has no CPU path (render.py:217 asserts CUDA); this arm "
-                           "times the CPU restatement of its arithmetic on the host cores"},
+        "config": workload_config(wl, args.gpus),
+        "note": "the reference has no CPU path (render.py:217 asserts CUDA): `value` times the CPU "
+                "restatement of its arithmetic on the host cores; `reference_gpu` is the "
+                "reference's own Triton path on this GPU",
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "reference_gpu": ref_gpu,
         "gpu_launches": 0,
     }
     emit(line)
@@ -262,9 +370,11 @@ def run_ours(args, wl):
     H, W, N, P = wl["H"], wl["W"], wl["N"], wl["P"]
     K, Wm = args.steps, args.warmup
     t_np = synth.synthetic_target_np(H, W, 0)
-    m_np = synth.importance_mask_np(t_np) if wl["mask"] else None
     target = torch.from_numpy(t_np).to(dev)
-    mask = None if m_np is None else torch.from_numpy(m_np).to(dev)
+    # the weight mask of algorithm.py:42-49, computed on the device by the library
+    mask = ggs_b200.importance_mask(target, H, W, edge_scales=(1, 2, 4), w_edge=0.7, w_var=0.3,
+                                    gamma=0.7, floor=0.15, smooth=3, strength=0.7) if wl["mask"] else None
+    m_np = None if mask is None else mask.cpu().numpy()
 
     # Each rank owns its shard of the population (weak scaling: P candidates per GPU).  POOL
     # distinct populations are rotated so consecutive steps never read the same genomes.
@@ -338,6 +448,38 @@ def run_ours(args, wl):
     chk = ggs_b200.fitness(pool[(Wm + K - 1) % POOL], target, H, W, 3.0, weight_mask=mask)
     assert torch.equal(chk.cpu(), out), "host path disagrees with device path"
 
+    # ---- N > 1: the gathered vector must equal a single-GPU evaluation of the same candidates,
+    # bit for bit (outside the timed region): rank 0 regenerates every rank's shard of the last
+    # step and evaluates it alone.
+    gather_ok = None
+    if world > 1:
+        r_last = (Wm + K - 1) % POOL
+        if rank == 0:
+            whole = torch.cat([torch.from_numpy(synth.new_population_np(P, N, H, W, seed=42 + 1000 * q + r_last))
+                               for q in range(world)]).to(dev)
+            alone = ggs_b200.fitness(whole, target, H, W, 3.0, weight_mask=mask)
+            gather_ok = bool(torch.equal(alone, last))
+            del whole
+            assert gather_ok, "gathered fitness vector differs from the single-GPU evaluation"
+        dist.barrier()
+
+    # ---- N == 1: the reference's real (Triton) path on this GPU, live, and parity against it
+    ref_gpu = None
+    if world == 1 and not args.no_reference_gpu:
+        ref_gpu, ref_npz = reference_gpu_live(args, wl, local_rank)
+        if ref_npz and os.path.exists(ref_npz):
+            z = np.load(ref_npz)
+            rm = torch.from_numpy(z["mask"]).to(dev) if wl["mask"] else None
+            ours = ggs_b200.fitness(pool[0], target, H, W, 3.0, weight_mask=rm).double().cpu().numpy()
+            theirs = z["fitness"]
+            ra, rb = np.argsort(theirs, kind="stable"), np.argsort(ours, kind="stable")
+            ref_gpu["parity_vs_this_library"] = {
+                "candidates": int(P), "fitness_max_rel_diff": float(np.abs(ours / theirs - 1.0).max()),
+                "ranking_positions_differing": int((ra != rb).sum()),
+                "top8_identical": bool(np.array_equal(ra[:8], rb[:8])),
+                "note": "same genomes (seed 42), same target, the reference's own mask"}
+            ref_gpu["speedup_e2e_list_api"] = None  # filled below once e2e is known
+
     t_max = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
@@ -349,17 +491,31 @@ def run_ours(args, wl):
         flops_timed = sum(flop_per_launch[(Wm + i) % POOL] for i in range(K))
         raster_s = kt["raster_ms"] * 1e-3
         achieved = flops_timed / raster_s / 1e12 if raster_s > 0 else None
+        peak = float(peaks["ffma_tflops"])
+        # flops the kernel really spends per EVALUATED pixel-splat pair:
+        # recurrence path 100 per 8 pixels (15 FFMA2, 9 FMUL2, 4 FADD2, 8 scalar FP, 4 MUFU),
+        # exact path 2 Horner FFMA2 + 2 MUFU + 5 blend operations per pixel pair + the set-up
+        real_flop = 12.5 * work["recurrence_pairs"] + 17.0 * work["exact_pairs"]
         roofline = {
             "bound": "fp32", "kernel": "ggs::raster_kernel", "achieved": achieved,
-            "peak": NOMINAL_FP32_TFLOPS, "unit": "TFLOP/s",
-            "frac": None if achieved is None else achieved / NOMINAL_FP32_TFLOPS,
+            "peak": peak, "unit": "TFLOP/s",
+            "frac": None if achieved is None else achieved / peak,
             "traffic": ncu_traffic(args.workload, P),
-            "peak_source": "nominal 148 SM x 128 lanes x 2 x clocks.max.sm 1965 MHz; "
-                           "MEASURED_PEAKS.json has no fp32 entry (HBM and bf16 tensor only)",
+            "peak_source": "scalar FFMA rate measured on this GPU by ggs_probe_peaks in this run "
+                           "(MEASURED_PEAKS.json has HBM and bf16 tensor entries only, no fp32); "
+                           "nominal = 148 SM x 128 lanes x 2 x clocks.max.sm 1965 MHz",
+            "nominal_fp32_tflops": NOMINAL_FP32_TFLOPS,
+            "frac_of_nominal": None if achieved is None else achieved / NOMINAL_FP32_TFLOPS,
             "measured_ffma_tflops": peaks["ffma_tflops"],
             "measured_ffma2_tflops": peaks["ffma2_tflops"],
             "measured_mufu_ex2_gops": peaks["mufu_ex2_gops"],
-            "frac_of_measured_ffma": None if achieved is None else achieved / peaks["ffma_tflops"],
+            "evaluated_pairs": work["pairs"],
+            "frac_evaluated": (real_flop / (kt["raster_ms"] / max(1, kt["evaluations"]) * 1e-3) / 1e12 / peak
+                               if kt["raster_ms"] > 0 else None),
+            "frac_evaluated_note": "flops the kernel really executes on the pairs it evaluates "
+                                   "(12.5 per pair on the recurrence path, 17 on the exact path) / "
+                                   "raster time / peak: survives the saturation stop, unlike `frac`, "
+                                   "which credits the reference's 23 flops for every in-AABB pair",
             "algorithmic_flop_per_launch": float(np.mean(flop_per_launch)),
             "pairs_per_candidate": float(np.mean(pairs)) / P,
             "evaluated_pairs_per_candidate": work["pairs"] / P,
@@ -381,26 +537,21 @@ def run_ours(args, wl):
                                  f"(oracle/ggs_oracle.c, OpenMP over candidates, scalar expf)"}
             except Exception as e:
                 log(f"[bench] cpu_baseline failed: {e}")
+        if ref_gpu and "value" in ref_gpu:
+            ref_gpu["speedup_e2e_list_api"] = e2e_value / ref_gpu["value"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms_all / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": wl["desc"], "H": H, "W": W, "splats": N,
-                       "population_per_gpu": P, "population_total": world * P,
-                       "fitness": "mask" if wl["mask"] else "plain", "k_sigma": 3.0,
-                       "parallelism": f"population sharded over {world} GPU(s), NCCL all-gather of "
-                                      f"the fitness vector" if world > 1 else "1 GPU",
-                       "l2": f"inputs rotate over {POOL} populations ({pool_bytes / 1e6:.0f} MB "
-                             f"> 126 MB L2)" if pool_bytes > 126e6 else
-                             f"inputs rotate over {POOL} populations ({pool_bytes / 1e6:.0f} MB); "
-                             f"compute-bound, {N * 36} B of genome per candidate"},
+            "config": workload_config(wl, world),
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": P * N * 9 * 4, "d2h_bytes_per_step": P * 4,
                     "ms_per_step": e2e_ms_all / K,
                     "api": "ggs_ctx_fitness_host (C ABI, pinned host genomes in, host fitness out)"},
             "gpu_launches": 2 * K,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "reference_gpu_recorded": reference_gpu_recorded(args.workload) if world == 1 else None,
+            "reference_gpu": ref_gpu,
+            "gather_bit_identical": gather_ok,
         }
         emit(line)
     if world > 1:
@@ -413,7 +564,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--impl", choices=["ours", "reference", "reference-gpu-child"], default="ours")
+    ap.add_argument("--no-reference-gpu", action="store_true",
+                    help="skip the live run of the reference's Triton path (N = 1)")
+    ap.add_argument("--ref-out", default="", help=argparse.SUPPRESS)
+    ap.add_argument("--ref-budget", type=float, default=25.0, help=argparse.SUPPRESS)
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="c3")
     ap.add_argument("--population", type=int, default=None, help="override candidates per GPU")
     ap.add_argument("--side", type=int, default=None, help="override H = W (roofline sweep)")
@@ -435,6 +590,8 @@ def main():
         POOL = args.pool
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] note: fewer than 3 warm-up steps requested")
+    if args.impl == "reference-gpu-child":
+        return run_reference_gpu_child(args, wl)
     return run_reference(args, wl) if args.impl == "reference" else run_ours(args, wl)
 
 
