@@ -22,12 +22,48 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
-bool pdl_enabled()
+// ---- run-time options: defaults from the environment (read once), changed by ggs_set_option ----
+struct Options {
+    int pdl;    // programmatic dependent launch between the kernels of a step (GGS_B200_PDL, default 1)
+    int split;  // CTAs per (candidate, tile): 0 = automatic (GGS_B200_SPLIT)
+    int fuse;   // decode fused into the raster: -1 = automatic, 0 / 1 (GGS_B200_FUSE)
+};
+static int env_int(const char *name, int fallback)
 {
-    // read on every launch (a getenv is nanoseconds next to a launch) so a test or a timing
-    // script can flip it inside one process
-    const char *v = getenv("GGS_B200_PDL");
-    return !(v != nullptr && v[0] == '0');
+    const char *v = getenv(name);
+    return (v != nullptr && v[0] != '\0') ? atoi(v) : fallback;
+}
+static Options &options()
+{
+    static Options o = {env_int("GGS_B200_PDL", 1) != 0, env_int("GGS_B200_SPLIT", 0), env_int("GGS_B200_FUSE", -1)};
+    return o;
+}
+
+bool pdl_enabled() { return options().pdl != 0; }
+
+static int wave_slots()
+{
+    // CTAs of the raster resident at once on the current device: 8 per SM (64 registers x 128 threads)
+    static int per_device[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148 * 8;
+    if (per_device[dev] == 0) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        per_device[dev] = sms * 8;
+    }
+    return per_device[dev];
+}
+
+int choose_split(int B, int N, int H, int W)
+{
+    const int forced = options().split;
+    if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
+    const int64_t ctas = (int64_t)B * tiles_x(W) * tiles_y(H);
+    const int slots = wave_slots();
+    int k = 1;
+    while (k < kMaxSplit && ctas * (k * 2) <= slots && (N + 2 * k - 1) / (2 * k) >= 16) k *= 2;
+    return k;
 }
 
 static int cuda_fail(cudaError_t e, const char *what)
@@ -42,31 +78,33 @@ static int cuda_fail(cudaError_t e, const char *what)
         if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
     } while (0)
 
+// Workspace layout: [ticket counters | records | cull boxes | partials].  The counters come first
+// so that their place does not depend on N, H, W: an owner that cleared the head of its buffer
+// once can vouch for them whatever it evaluates next (EvalOptions::counters_zeroed).
 size_t workspace_bytes(int B, int N, int H, int W)
 {
     const size_t S = (size_t)B * (size_t)N;
     const size_t nt = (size_t)tiles_x(W) * tiles_y(H);
     size_t n = 0;
+    n += align_up((size_t)B * sizeof(int), 256);
     n += align_up(S * sizeof(SplatRec), 256);
     n += align_up(S * sizeof(uint2), 256);
-    n += align_up((size_t)B * nt * sizeof(float2), 256);
-    n += align_up((size_t)B * sizeof(int), 256);
+    n += align_up((size_t)B * nt * kMaxSplit * sizeof(float2), 256);
     return n;
 }
 
 Workspace carve_workspace(void *base, int B, int N, int H, int W)
 {
     const size_t S = (size_t)B * (size_t)N;
-    const size_t nt = (size_t)tiles_x(W) * tiles_y(H);
     char *p = static_cast<char *>(base);
     Workspace ws;
+    ws.counter = reinterpret_cast<int *>(p);
+    p += align_up((size_t)B * sizeof(int), 256);
     ws.rec = reinterpret_cast<float4 *>(p);
     p += align_up(S * sizeof(SplatRec), 256);
     ws.aabb = reinterpret_cast<uint2 *>(p);
     p += align_up(S * sizeof(uint2), 256);
     ws.partial = reinterpret_cast<float2 *>(p);
-    p += align_up((size_t)B * nt * sizeof(float2), 256);
-    ws.counter = reinterpret_cast<int *>(p);
     return ws;
 }
 
@@ -104,8 +142,11 @@ struct TimingLog {
     int created = 0;    // event triples created so far
     cudaEvent_t ev[kCap][3];
 };
-static TimingLog g_timing;
-static unsigned long long *g_stats = nullptr;  // ggs_stats_target(): device counters or NULL
+// Both belong to the calling thread: an evaluation issued by another thread (another device, an
+// engine on its own stream) is neither timed nor switched to the instrumented kernel.
+static thread_local TimingLog g_timing;
+static thread_local unsigned long long *g_stats = nullptr;  // ggs_stats_target(): device counters or NULL
+static thread_local int g_stats_device = -1;
 
 static cudaEvent_t *timing_slot()
 {
@@ -118,11 +159,13 @@ static cudaEvent_t *timing_slot()
     return g_timing.ev[g_timing.used++];
 }
 
-// decode + raster on `stream`; the one launch sequence behind every public entry.
+// decode + raster (or the fused raster alone) on `stream`; the one launch sequence behind every
+// public entry.
 int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
-                    float k_sigma, const float bg[3], const float *d_target, const float *d_mask,
-                    int mode, float beta, float *d_fitness, void *d_images, int image_u8,
-                    void *d_workspace, size_t workspace_bytes_given, cudaStream_t stream)
+             float k_sigma, const float bg[3], const float *d_target, const float *d_mask,
+             int mode, float beta, float *d_fitness, void *d_images, int image_u8,
+             void *d_workspace, size_t workspace_bytes_given, cudaStream_t stream,
+             const EvalOptions &opt)
 {
     if (B == 0) return GGS_OK;
     if (d_genomes == nullptr && N > 0) {
@@ -138,14 +181,51 @@ int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, 
         set_error("workspace must be 256-byte aligned");
         return GGS_EINVAL;
     }
-    const Workspace ws = carve_workspace(d_workspace, B, N, H, W);
+    if (opt.split != 0 && opt.split != 1 && opt.split != 2 && opt.split != 4 && opt.split != 8) {
+        set_error("split must be 0 (automatic), 1, 2, 4 or 8 (got %d)", opt.split);
+        return GGS_EINVAL;
+    }
+    RasterLaunch q;
+    q.ws = carve_workspace(d_workspace, B, N, H, W);
+    q.B = B;
+    q.N = N;
+    q.H = H;
+    q.W = W;
+    q.bg[0] = bg[0];
+    q.bg[1] = bg[1];
+    q.bg[2] = bg[2];
+    q.d_target = d_target;
+    q.d_mask = d_mask;
+    q.mode = mode;
+    q.beta = beta;
+    q.d_fitness = d_fitness;
+    q.d_images = d_images;
+    q.image_u8 = image_u8;
+    q.d_genomes = d_genomes;
+    q.layout = layout;
+    q.cols = cols;
+    q.k_sigma = k_sigma;
+    q.peers = opt.peers;
+    // the instrumented kernel exists for the throughput path only
+    int dev = -1;
+    const bool stats = g_stats != nullptr && cudaGetDevice(&dev) == cudaSuccess && dev == g_stats_device;
+    q.d_stats = stats ? g_stats : nullptr;
+    q.split = stats ? 1 : (opt.split != 0 ? opt.split : choose_split(B, N, H, W));
+    const int fuse = stats ? 0 : (opt.fuse >= 0 ? opt.fuse : options().fuse);
+    const int64_t ctas = (int64_t)B * tiles_x(W) * tiles_y(H) * q.split;
+    q.fused = N > 0 && fuse != 0 && fused_decode_possible(N, q.split) && (fuse == 1 || ctas <= wave_slots());
+
     cudaEvent_t *ev = timing_slot();
     if (ev) GGS_CUDA(cudaEventRecord(ev[0], stream));
-    GGS_CUDA(launch_decode(d_genomes, layout, (int64_t)B * N, cols, H, W, k_sigma, ws.rec, ws.aabb,
-                           nullptr, nullptr, ws.counter, B, stream));
+    if (q.fused) {
+        // no decode launch clears the ticket counters: do it here unless their owner vouches for them
+        if (!opt.counters_zeroed) GGS_CUDA(cudaMemsetAsync(q.ws.counter, 0, (size_t)B * sizeof(int), stream));
+    } else {
+        GGS_CUDA(launch_decode(d_genomes, layout, (int64_t)B * N, cols, H, W, k_sigma, q.ws.rec, q.ws.aabb,
+                               nullptr, nullptr, q.ws.counter, B, stream));
+    }
     if (ev) GGS_CUDA(cudaEventRecord(ev[1], stream));
-    GGS_CUDA(launch_raster(ws, B, N, H, W, bg, d_target, d_mask, mode, beta, d_fitness, d_images,
-                           image_u8, g_stats, stream));
+    GGS_CUDA(launch_raster(q, stream));
     if (ev) GGS_CUDA(cudaEventRecord(ev[2], stream));
     return GGS_OK;
 }
@@ -238,10 +318,10 @@ int ggs_render_u8(const float *d_genomes, int layout, int B, int N, int cols, in
                     workspace_bytes_given, static_cast<cudaStream_t>(stream));
 }
 
-int ggs_fitness(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
-                float k_sigma, const float *d_target, const float *d_mask, int mode,
-                float boost_beta, float *d_fitness, float *d_images, void *d_workspace,
-                size_t workspace_bytes_given, void *stream)
+int ggs_fitness_ex(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
+                   float k_sigma, const float *d_target, const float *d_mask, int mode,
+                   float boost_beta, float *d_fitness, float *d_images, void *d_workspace,
+                   size_t workspace_bytes_given, int split, void *stream)
 {
     int rc = check_layout(layout);
     if (rc) return rc;
@@ -260,9 +340,20 @@ int ggs_fitness(const float *d_genomes, int layout, int B, int N, int cols, int 
         return GGS_EINVAL;
     }
     const float white[3] = {1.0f, 1.0f, 1.0f};  // render.py:209
+    EvalOptions opt;
+    opt.split = split;
     return evaluate(d_genomes, layout, B, N, cols, H, W, k_sigma, white, d_target, d_mask, mode,
                     boost_beta, d_fitness, d_images, 0, d_workspace, workspace_bytes_given,
-                    static_cast<cudaStream_t>(stream));
+                    static_cast<cudaStream_t>(stream), opt);
+}
+
+int ggs_fitness(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
+                float k_sigma, const float *d_target, const float *d_mask, int mode,
+                float boost_beta, float *d_fitness, float *d_images, void *d_workspace,
+                size_t workspace_bytes_given, void *stream)
+{
+    return ggs_fitness_ex(d_genomes, layout, B, N, cols, H, W, k_sigma, d_target, d_mask, mode,
+                          boost_beta, d_fitness, d_images, d_workspace, workspace_bytes_given, 0, stream);
 }
 
 /* ---------------------------------------------------------------------------------- */
@@ -426,10 +517,20 @@ int ggs_ctx_fitness_host(ggs_ctx *c, const float *h_genomes, int layout, int B, 
               std::max<size_t>((size_t)B * row_bytes, 256));
     if (rc) return rc;
     for (int k = 0; k < ns; ++k) {
+        const size_t had = c->ws_cap[k];
         rc = grow(&c->d_ws[k], &c->ws_cap[k], workspace_bytes(start[k + 1] - start[k], N, c->H, c->W));
         if (rc) return rc;
+        // a fresh buffer: clear it once, every evaluation leaves its ticket counters at zero
+        if (c->ws_cap[k] != had) GGS_CUDA(cudaMemsetAsync(c->d_ws[k], 0, c->ws_cap[k], c->stream[k & 1]));
     }
     const float white[3] = {1.0f, 1.0f, 1.0f};
+    // One kernel configuration for the whole call, chosen from the WHOLE batch: the result does
+    // not depend on how the batch is sliced and equals ggs_fitness on the same genomes.
+    EvalOptions opt;
+    opt.split = choose_split(B, N, c->H, c->W);
+    opt.fuse = (fused_decode_possible(N, opt.split) &&
+                (int64_t)B * tiles_x(c->W) * tiles_y(c->H) * opt.split <= wave_slots()) ? 1 : 0;
+    opt.counters_zeroed = true;
     for (int k = 0; k < ns; ++k) {
         const size_t off = (size_t)start[k] * N * cols;
         GGS_CUDA(cudaMemcpyAsync(c->d_genomes + off, h_genomes + off,
@@ -442,7 +543,7 @@ int ggs_ctx_fitness_host(ggs_ctx *c, const float *h_genomes, int layout, int B, 
         GGS_CUDA(cudaStreamWaitEvent(c->stream[s], c->landed[k], 0));
         rc = evaluate(c->d_genomes + (size_t)start[k] * N * cols, layout, sb, N, cols, c->H, c->W,
                       k_sigma, white, c->d_target, c->d_mask, mode, boost_beta,
-                      c->d_fitness + start[k], nullptr, 0, c->d_ws[k], c->ws_cap[k], c->stream[s]);
+                      c->d_fitness + start[k], nullptr, 0, c->d_ws[k], c->ws_cap[k], c->stream[s], opt);
         if (rc) return rc;
     }
     // Drain: stream 1's work must finish before the single D2H issued on stream 0.
@@ -523,7 +624,31 @@ int ggs_importance_mask(const float *d_image, int H0, int W0, int H, int W, int 
 int ggs_stats_target(unsigned long long *d_counters2)
 {
     g_stats = d_counters2;
+    g_stats_device = -1;
+    if (d_counters2 != nullptr) GGS_CUDA(cudaGetDevice(&g_stats_device));
     return GGS_OK;
+}
+
+int ggs_set_option(const char *name, int value)
+{
+    if (name != nullptr && strcmp(name, "pdl") == 0) {
+        options().pdl = value != 0;
+    } else if (name != nullptr && strcmp(name, "split") == 0 &&
+               (value == 0 || value == 1 || value == 2 || value == 4 || value == 8)) {
+        options().split = value;
+    } else if (name != nullptr && strcmp(name, "fuse") == 0 && value >= -1 && value <= 1) {
+        options().fuse = value;
+    } else {
+        set_error("ggs_set_option: unknown option or value (%s = %d)", name ? name : "(null)", value);
+        return GGS_EINVAL;
+    }
+    return GGS_OK;
+}
+
+int ggs_choose_split(int B, int N, int H, int W)
+{
+    if (B < 1 || N < 0 || H < 1 || W < 1) return 1;
+    return choose_split(B, N, H, W);
 }
 
 int ggs_timing_enable(int enable)

@@ -30,6 +30,11 @@ constexpr int kThreads = kWarps * 32;
 #endif
 constexpr int kListCap = GGS_LIST_CAP;  // staged splat records per flush (48 B each)
 
+// Latency path: up to kMaxSplit CTAs (one thread-block cluster) share a (candidate, tile), each
+// compositing one segment of the genome (ggs_raster.cu, raster_split_kernel).
+constexpr int kMaxSplit = 8;   // portable cluster size limit
+static_assert(kTileH % kMaxSplit == 0, "every CTA of a cluster finishes an equal share of the tile's rows");
+
 constexpr int kDecodeThreads = 256;
 constexpr int kDecodeStageMaxCols = 16;
 
@@ -49,8 +54,23 @@ static_assert(sizeof(SplatRec) == 48, "SplatRec must be 3 float4");
 struct Workspace {
     float4 *rec;      // [B*N*3]
     uint2 *aabb;      // [B*N]   x0|x1<<16, y0|y1<<16 (int16 each)
-    float2 *partial;  // [B*ntiles] (numerator, denominator) per tile
-    int *counter;     // [B] tiles finished per candidate
+    float2 *partial;  // [B*ntiles*kMaxSplit] (numerator, denominator) per CTA
+    int *counter;     // [B] CTAs finished per candidate (zero between launches)
+};
+
+// Fitness stores into the gathered vectors of the other GPUs of the box (ggs_peers.cu): the CTA
+// that finishes a candidate writes its fitness straight into every rank's peer-mapped buffer, and
+// the CTA that finishes the launch's last candidate raises this rank's flag on every rank.  No
+// collective launch follows the raster.  n == 0 switches it off.
+constexpr int kMaxPeers = 8;
+struct PeerStores {
+    int n = 0;                    // ranks that receive the values (world size), 0 = off
+    int rank = 0;                 // this rank
+    int offset = 0;               // index of this launch's candidate 0 in the gathered vector
+    unsigned epoch = 0;           // value of the flags once the whole launch has been stored
+    float *fit[kMaxPeers] = {};      // rank r's gathered vector of this epoch (own buffer for r == rank)
+    unsigned *flag[kMaxPeers] = {};  // rank r's arrival flags, one per sender
+    int *done = nullptr;          // candidates published by this launch (local, self-resetting)
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -69,10 +89,26 @@ cudaError_t launch_encode(const float *d_axes, int64_t rows, int cols, float *d_
                           cudaStream_t stream);
 
 // raster.cu
-cudaError_t launch_raster(const Workspace &ws, int B, int N, int H, int W, const float bg[3],
-                          const float *d_target, const float *d_mask, int mode, float beta,
-                          float *d_fitness, void *d_images, int image_u8,
-                          unsigned long long *d_stats, cudaStream_t stream);
+struct RasterLaunch {
+    Workspace ws;
+    int B = 0, N = 0, H = 0, W = 0;
+    float bg[3] = {1.0f, 1.0f, 1.0f};
+    const float *d_target = nullptr, *d_mask = nullptr;
+    int mode = GGS_MODE_PLAIN;
+    float beta = 1.0f;
+    float *d_fitness = nullptr;
+    void *d_images = nullptr;
+    int image_u8 = 0;
+    unsigned long long *d_stats = nullptr;
+    int split = 1;        // CTAs per (candidate, tile): 1, 2, 4 or 8
+    bool fused = false;   // decode inside the raster (needs the genomes, ceil(N / split) <= kListCap)
+    const float *d_genomes = nullptr;
+    int layout = GGS_LAYOUT_AXES_ANGLE, cols = 9;
+    float k_sigma = 3.0f;
+    PeerStores peers;
+};
+cudaError_t launch_raster(const RasterLaunch &q, cudaStream_t stream);
+bool fused_decode_possible(int N, int split);
 
 // breed.cu
 // Children [0, n_children) of the step are produced (counter-based streams: child c is the same
@@ -110,6 +146,43 @@ bool pdl_enabled();  // api.cu
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
 
+// A fitness value has been computed for candidate `b` of a launch of B candidates.
+__device__ __forceinline__ void peer_publish(const PeerStores &p, int b, float fit, int B)
+{
+    if (p.n == 0) return;
+    for (int r = 0; r < p.n; ++r)
+        asm volatile("st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p.fit[r] + p.offset + b), "f"(fit) : "memory");
+    __threadfence_system();
+    if (atomicAdd(p.done, 1) == B - 1) {  // every candidate of this launch is stored everywhere
+        atomicExch(p.done, 0);
+        __threadfence_system();
+        for (int r = 0; r < p.n; ++r)
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flag[r] + p.rank), "r"(p.epoch) : "memory");
+    }
+}
+
+// Same, for a launch that runs as thread-block clusters of `cluster` CTAs along x.
+template <typename... P, typename... A>
+inline cudaError_t launch_kernel_cluster(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem,
+                                         int cluster, cudaStream_t stream, A... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 template <typename... P, typename... A>
 inline cudaError_t launch_kernel(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem,
                                  cudaStream_t stream, A... args)
@@ -128,10 +201,22 @@ inline cudaError_t launch_kernel(void (*kernel)(P...), dim3 grid, dim3 block, si
 }
 #endif
 
-// api.cu: decode + raster on `stream`, the launch sequence behind every evaluation entry.
+// api.cu: the launch sequence behind every evaluation entry -- decode + raster, or the raster's
+// fused-decode variant alone -- on `stream`.
+struct EvalOptions {
+    int split = 0;   // CTAs per (candidate, tile): 0 = choose_split() for this B, else 1 / 2 / 4 / 8
+    int fuse = -1;   // decode inside the raster: -1 = when it pays (one wave) and fits, 0 = never, 1 = if it fits
+    bool counters_zeroed = false;  // the workspace's ticket counters are known to be zero (its owner
+                                   // cleared them once; every launch leaves them zero)
+    PeerStores peers;
+};
 int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
              float k_sigma, const float bg[3], const float *d_target, const float *d_mask,
              int mode, float beta, float *d_fitness, void *d_images, int image_u8,
-             void *d_workspace, size_t workspace_bytes_given, cudaStream_t stream);
+             void *d_workspace, size_t workspace_bytes_given, cudaStream_t stream,
+             const EvalOptions &opt = EvalOptions());
+// Largest split (1, 2, 4, 8) that keeps B * tiles * split CTAs within one wave of the device and
+// every genome segment worth a CTA; the policy behind split = 0.
+int choose_split(int B, int N, int H, int W);
 
 }  // namespace ggs

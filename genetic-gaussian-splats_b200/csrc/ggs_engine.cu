@@ -212,6 +212,15 @@ __global__ void __launch_bounds__(kSelectThreads) metropolis_kernel(MetropolisPa
     if (s_cur >= 0) copy_row(q.current, q.cand + s_cur * row, row, threadIdx.x, kSelectThreads);
 }
 
+// The engines own their workspace, cleared once at creation: the ticket counters at its head are
+// zero before every evaluation, so the fused raster needs no memset in front of it.
+EvalOptions owned_workspace()
+{
+    EvalOptions o;
+    o.counters_zeroed = true;
+    return o;
+}
+
 int fail(cudaError_t e, const char *what)
 {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -326,6 +335,7 @@ int ggs_ga_create(int device, int P, int N, int H, int W, int n_elite, int max_g
     if (e == cudaSuccess) e = cudaMalloc(&g->target, (size_t)H * W * 3 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&g->mask, (size_t)H * W * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&g->ws, g->ws_bytes);
+    if (e == cudaSuccess) e = cudaMemset(g->ws, 0, g->ws_bytes);  // ticket counters start at zero
     if (e == cudaSuccess) e = cudaMalloc(&g->curves, (size_t)g->capacity * 3 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&g->best_ind, (size_t)N * 9 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&g->best_fit, sizeof(double));
@@ -397,7 +407,7 @@ int ggs_ga_start(ggs_ga *g, const float *d_population, int cols, uint64_t seed, 
     const float bg[3] = {1.0f, 1.0f, 1.0f};
     int rc = evaluate(g->room[0], GGS_LAYOUT_AXES_ANGLE, g->P, g->N, 9, g->H, g->W, g->k_sigma, bg,
                       g->target, g->mode == GGS_MODE_PLAIN ? nullptr : g->mask, g->mode, g->beta,
-                      g->child_fit, nullptr, 0, g->ws, g->ws_bytes, st);
+                      g->child_fit, nullptr, 0, g->ws, g->ws_bytes, st, owned_workspace());
     if (rc) return rc;
     const double inf = INFINITY;
     const int zero = 0;
@@ -441,7 +451,7 @@ int ggs_ga_run(ggs_ga *g, int count, const float *h_sigma6, int tour_k, float cx
                              g->seed, (uint32_t)gen, st));
         int rc = evaluate(children, GGS_LAYOUT_AXES_ANGLE, keep, g->N, 9, g->H, g->W, g->k_sigma, bg,
                           g->target, g->mode == GGS_MODE_PLAIN ? nullptr : g->mask, g->mode,
-                          g->beta, g->child_fit, nullptr, 0, g->ws, g->ws_bytes, st);
+                          g->beta, g->child_fit, nullptr, 0, g->ws, g->ws_bytes, st, owned_workspace());
         if (rc) return rc;
         rc = ga_rank(g, g->n_elite, nb, st);
         if (rc) return rc;
@@ -559,6 +569,7 @@ int ggs_sa_create(int device, int N, int H, int W, int tries, int max_iterations
     if (e == cudaSuccess) e = cudaMalloc(&g->target, (size_t)H * W * 3 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&g->mask, (size_t)H * W * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&g->ws, g->ws_bytes);
+    if (e == cudaSuccess) e = cudaMemset(g->ws, 0, g->ws_bytes);  // ticket counters start at zero
     if (e == cudaSuccess) e = cudaMalloc(&g->curves, (size_t)g->capacity * 2 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&g->e_current, sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&g->e_best, sizeof(double));
@@ -612,7 +623,7 @@ static int sa_energy(ggs_sa *g, const float *genomes, int B, cudaStream_t st)
     const float bg[3] = {1.0f, 1.0f, 1.0f};
     return evaluate(genomes, GGS_LAYOUT_AXES_ANGLE, B, g->N, 9, g->H, g->W, g->k_sigma, bg, g->target,
                     g->mode == GGS_MODE_PLAIN ? nullptr : g->mask, g->mode, g->beta, g->energy,
-                    nullptr, 0, g->ws, g->ws_bytes, st);
+                    nullptr, 0, g->ws, g->ws_bytes, st, owned_workspace());
 }
 
 int ggs_sa_start(ggs_sa *g, const float *d_state, int cols, uint64_t seed, void *stream)

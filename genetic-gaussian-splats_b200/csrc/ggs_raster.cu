@@ -37,7 +37,24 @@
 //     MOVs per splat (tests/test_cpu_sass.py guards this);
 //   * per-thread constants used in the loop are routed through a shuffle so ptxas cannot
 //     rematerialise them from %tid.x once per list entry.
-#include "ggs_common.cuh"
+//
+// Two kernels share the list building, the composite and the epilogue below:
+//   raster_kernel        one CTA per (candidate, tile): the throughput path (populations);
+//   raster_split_kernel  the latency path for small batches (SA neighbours, a 32-individual GA,
+//                        single frames), where one CTA per tile leaves most of the GPU idle: a
+//                        thread-block CLUSTER of K = 2 / 4 / 8 CTAs shares a tile, CTA k composites
+//                        the k-th segment of the genome front to back on its own, and the K partial
+//                        (colour, transmittance) states -- "over" is associative:
+//                        (C1,T1) o (C2,T2) = (C1 + T1 C2, T1 T2) -- are folded in genome order
+//                        through distributed shared memory, each CTA finishing 1/K of the tile's
+//                        pixels.  Its fused variant also decodes the genome rows itself (the
+//                        arithmetic of ggs_decode_math.cuh), so an evaluation is ONE launch.
+// This file is compiled with -fmad=false (ggs_decode_math.cuh): every FMA below is explicit.
+#include <cooperative_groups.h>
+
+#include "ggs_decode_math.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace ggs {
 namespace {
@@ -55,15 +72,6 @@ static_assert(GGS_SCAN_CHUNK <= kListCap, "a scan round must fit the list");
 constexpr int kScanChunk = kThreads * kScanPerThread;
 #ifndef GGS_SAT_EVERY
 #define GGS_SAT_EVERY 8
-#endif
-#ifndef GGS_BOX_PREFETCH
-#define GGS_BOX_PREFETCH 1
-#endif
-#ifndef GGS_DENSE_STAGE
-#define GGS_DENSE_STAGE 1
-#endif
-#if GGS_DENSE_STAGE && !GGS_BOX_PREFETCH
-#error "GGS_DENSE_STAGE needs GGS_BOX_PREFETCH"
 #endif
 constexpr int kSatEvery = GGS_SAT_EVERY;                 // list entries between saturation votes
 constexpr float kOpaque = 2.384185791015625e-07f;        // 2^-22: transmittance counted as zero
@@ -270,73 +278,91 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
     return true;
 }
 
-template <bool kStats>
-__global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS)
-raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, int N, int H, int W,
-              int ntx, int ntiles, float bg_r, float bg_g, float bg_b,
-              const float *__restrict__ target, const float *__restrict__ mask, int mode,
-              float beta, float *__restrict__ images, int image_u8, float2 *__restrict__ partial,
-              int *__restrict__ counter, float *__restrict__ fitness,
-              unsigned long long *__restrict__ stats)
+// ------------------------------------------------------------------------------------------
+// Kernel arguments (one struct for both kernels).
+struct RasterArgs {
+    // two-kernel path: records and cull boxes written by decode_kernel
+    const float4 *rec;   // [B][N][3]
+    const uint2 *aabb;   // [B][N]
+    // fused path: the genomes themselves
+    const float *genomes;  // [B][N][cols]
+    int cols;
+    float k_sigma;
+    int N, H, W, ntx, ntiles;
+    float bg_r, bg_g, bg_b;
+    const float *target;  // [H][W][3] or NULL (render only)
+    const float *mask;    // [H][W] or NULL
+    int mode;
+    float beta;
+    float *images;  // [B][H][W][3] float or uint8, or NULL
+    int image_u8;
+    float2 *partial;  // [B][ntiles][split]
+    int *counter;     // [B], zero at kernel start, zero again at kernel end
+    float *fitness;   // [B]
+    unsigned long long *stats;
+    int split;  // CTAs per (candidate, tile): the cluster size of raster_split_kernel
+    PeerStores peers;  // fitness stores into the other GPUs' gathered vectors (ggs_peers.cu)
+};
+
+struct TileGeom {
+    int b, X0, Y0, X1, Y1, X, Yb;
+    float Xf, Ybf;
+    unsigned lanebit, band_sel;
+};
+
+__device__ __forceinline__ TileGeom tile_geometry(int cand_tile, int ntx, int ntiles, int lane, int warp)
 {
-    unsigned work[2] = {0u, 0u};  // kStats: row pairs blended on the recurrence / exact path
-    __shared__ float4 s_list[kListCap * 3];
-#if GGS_DENSE_STAGE
-    __shared__ int s_wcnt[2][kScanPerThread][kWarps];
-    __shared__ int s_idx[kListCap];
-#else
-    __shared__ int s_wcnt[kScanPerThread][kWarps];
-#endif
-    __shared__ float s_red[2 * kWarps];
-    __shared__ int s_last;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.x / ntiles;
-    const int t = blockIdx.x - b * ntiles;
+    TileGeom g;
+    g.b = cand_tile / ntiles;
+    const int t = cand_tile - g.b * ntiles;
     const int ty = t / ntx, tx = t - ty * ntx;
-    const int X0 = tx * kTileW, Y0 = ty * kTileH;
-    const int X1 = X0 + kTileW - 1, Y1 = Y0 + kTileH - 1;
-    const int X = X0 + lane, Yb = Y0 + warp * kRowsPerThread;
+    g.X0 = tx * kTileW;
+    g.Y0 = ty * kTileH;
+    g.X1 = g.X0 + kTileW - 1;
+    g.Y1 = g.Y0 + kTileH - 1;
+    g.X = g.X0 + lane;
+    g.Yb = g.Y0 + warp * kRowsPerThread;
     // Loop constants of the composite, pinned in registers by a (no-op) shuffle.
-    const float Xf = __shfl_sync(0xffffffffu, (float)X, lane);
-    const float Ybf = __shfl_sync(0xffffffffu, (float)Yb, lane);
-    const unsigned lanebit = __shfl_sync(0xffffffffu, 1u << lane, lane);
-    const unsigned band_sel = __shfl_sync(0xffffffffu, 0x4440u + (unsigned)warp, lane);  // PRMT: byte `warp`
+    g.Xf = __shfl_sync(0xffffffffu, (float)g.X, lane);
+    g.Ybf = __shfl_sync(0xffffffffu, (float)g.Yb, lane);
+    g.lanebit = __shfl_sync(0xffffffffu, 1u << lane, lane);
+    g.band_sel = __shfl_sync(0xffffffffu, 0x4440u + (unsigned)warp, lane);  // PRMT: byte `warp`
+    return g;
+}
 
-    // Transmittance starts at 1 inside the image and at 0 outside it: pixels beyond the image
-    // edge then take no colour and never keep a band from saturating.
-    GGS_PX_DECLARE();
-#define GGS_T_INIT(k)                                              \
-    GGS_PX_INIT(k, (X < W && Yb + 2 * k < H) ? 1.0f : 0.0f,        \
-                (X < W && Yb + 2 * k + 1 < H) ? 1.0f : 0.0f)
-    GGS_PAIRS(GGS_T_INIT)
-#undef GGS_T_INIT
+// Shared memory of a CTA (static, 29 KB): the staged list, the index list of the scan, the
+// per-warp hit counts of two rounds, the fitness reduction scratch.
+struct __align__(16) RasterSmem {
+    float4 list[kListCap * 3];
+    int idx[kListCap];
+    int wcnt[2][kScanPerThread][kWarps];
+    float red[2 * kWarps];
+    int last;
+};
+
+// Walk records [0, n) of `recb` / `boxb` from the last to the first (front to back) and blend
+// the ones that touch the tile.  Slot j of a round maps thread `tid` to record
+// top - 1 - (j*kThreads + tid): ascending (j, tid) is descending genome order, so the ordinary
+// ballot compaction yields the order we need.  A round only compacts the INDICES of the hits
+// (ordered, by ballot and a cross-warp prefix); the records are staged when the list is about
+// to be composited, one list entry per thread, so the staging code runs ceil(cnt / kThreads)
+// times per flush instead of once per (round, slot) with a few lanes active.
+template <bool kStats>
+__device__ __forceinline__ void scan_and_composite(const float4 *__restrict__ recb,
+                                                   const uint2 *__restrict__ boxb, int n,
+                                                   const TileGeom &g, RasterSmem &sm, int tid, int lane,
+                                                   int warp, unsigned (&work)[2])
+{
     bool live = true;  // warp-uniform: this band still has a non-opaque pixel
-
-    const float4 *recb = rec + (int64_t)b * N * 3;
-    const uint2 *boxb = aabb + (int64_t)b * N;
-    pdl_wait();  // the decode launch ahead of us has completed; nothing above reads memory
-    pdl_trigger();
-
-    // Walk the genome from its last splat to its first (front to back).  Slot j of a round
-    // maps thread `tid` to record  top - 1 - (j*kThreads + tid): ascending (j, tid) is
-    // descending genome order, so the ordinary ballot compaction yields the order we need.
     int cnt = 0;
-#if GGS_BOX_PREFETCH
     uint2 nbox[kScanPerThread];  // the round's boxes, loaded one round ahead
 #pragma unroll
     for (int j = 0; j < kScanPerThread; ++j) {
-        const int i0 = N - 1 - (j * kThreads + tid);
+        const int i0 = n - 1 - (j * kThreads + tid);
         nbox[j] = (i0 >= 0) ? __ldg(boxb + i0) : make_uint2(0xffff7fffu, 0xffff7fffu);
     }
-#endif
-#if GGS_DENSE_STAGE
-    // A round only compacts the INDICES of the splats that touch the tile (ordered, by ballot and
-    // a cross-warp prefix); the records are staged when the list is about to be composited, one
-    // list entry per thread, so the staging code runs ceil(cnt / kThreads) times per flush instead
-    // of once per (round, slot) with a few lanes active.
     int par = 0;
-    for (int top = N; top > 0; top -= kScanChunk) {
+    for (int top = n; top > 0; top -= kScanChunk) {
         bool hit[kScanPerThread];
         unsigned bal[kScanPerThread];
 #pragma unroll
@@ -344,9 +370,9 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
             const uint2 box = nbox[j];
             const int bx0 = (int)(short)(box.x & 0xffff), bx1 = (int)box.x >> 16;
             const int by0 = (int)(short)(box.y & 0xffff), by1 = (int)box.y >> 16;
-            hit[j] = (bx1 >= X0) & (bx0 <= X1) & (by1 >= Y0) & (by0 <= Y1);
+            hit[j] = (bx1 >= g.X0) & (bx0 <= g.X1) & (by1 >= g.Y0) & (by0 <= g.Y1);
             bal[j] = __ballot_sync(0xffffffffu, hit[j]);
-            if (lane == 0) s_wcnt[par][j][warp] = __popc(bal[j]);
+            if (lane == 0) sm.wcnt[par][j][warp] = __popc(bal[j]);
         }
 #pragma unroll
         for (int j = 0; j < kScanPerThread; ++j) {
@@ -360,11 +386,11 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
             int pre = 0, tot = 0;
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) {
-                const int c = s_wcnt[par][j][w];
+                const int c = sm.wcnt[par][j][w];
                 pre += (w < warp) ? c : 0;
                 tot += c;
             }
-            if (hit[j]) s_idx[run + pre + __popc(bal[j] & (lanebit - 1u))] = top - 1 - (j * kThreads + tid);
+            if (hit[j]) sm.idx[run + pre + __popc(bal[j] & (g.lanebit - 1u))] = top - 1 - (j * kThreads + tid);
             run += tot;
         }
         cnt = run;
@@ -372,177 +398,152 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
         if (cnt > kListCap - kScanChunk || top <= kScanChunk) {
             __syncthreads();
             for (int e = tid; e < cnt; e += kThreads) {
-                const int i = s_idx[e];
+                const int i = sm.idx[e];
                 const uint2 box = __ldg(boxb + i);
                 const float4 *src = recb + (int64_t)i * 3;
                 float4 q2 = __ldg(src + 2);
-                q2.y = __uint_as_float(lane_mask((int)(short)(box.x & 0xffff), (int)box.x >> 16, X0));
-                q2.z = __uint_as_float(row_code((int)(short)(box.y & 0xffff), (int)box.y >> 16, Y0,
+                q2.y = __uint_as_float(lane_mask((int)(short)(box.x & 0xffff), (int)box.x >> 16, g.X0));
+                q2.z = __uint_as_float(row_code((int)(short)(box.y & 0xffff), (int)box.y >> 16, g.Y0,
                                                 q2.w < 0.0f));
-                cp_async16(&s_list[e * 3 + 0], src + 0);  // LDGSTS: no register staging
-                cp_async16(&s_list[e * 3 + 1], src + 1);
-                s_list[e * 3 + 2] = q2;
+                cp_async16(&sm.list[e * 3 + 0], src + 0);  // LDGSTS: no register staging
+                cp_async16(&sm.list[e * 3 + 1], src + 1);
+                sm.list[e * 3 + 2] = q2;
             }
             cp_async_wait_all();
             __syncthreads();
-            if (live) live = composite_list<kStats>(s_list, cnt, lanebit, band_sel, Xf, Ybf, work);
+            if (live)
+                live = composite_list<kStats>(sm.list, cnt, g.lanebit, g.band_sel, g.Xf, g.Ybf, work);
             cnt = 0;
             // every band opaque: the rest of the genome is hidden behind what is drawn
             if (__syncthreads_and(!live)) break;
         }
     }
-#else
-    for (int top = N; top > 0; top -= kScanChunk) {
-        bool hit[kScanPerThread];
-        unsigned bal[kScanPerThread];
-        int idx[kScanPerThread];
-        int bx0[kScanPerThread], bx1[kScanPerThread], by0[kScanPerThread], by1[kScanPerThread];
+}
+
+// Fused decode (latency path): the CTA decodes rows [i_lo, i_lo + n) of the candidate's genome
+// itself, kThreads per round in descending order, and stages the ones that touch the tile
+// straight into the list (n <= kListCap, so there is a single composite).  Same arithmetic as
+// decode_kernel (ggs_decode_math.cuh), hence the same records and the same image bits as the
+// two-kernel path.
+template <bool kAxes>
+__device__ __forceinline__ int build_list_fused(const float *__restrict__ gb, int cols, int i_lo, int n,
+                                                int H, int W, float k_sigma, const TileGeom &g,
+                                                RasterSmem &sm, int tid, int lane, int warp)
+{
+    int cnt = 0, par = 0;
+    for (int top = n; top > 0; top -= kThreads) {
+        const int rel = top - 1 - tid;
+        bool hit = false;
+        SplatRec r;
+        int bx0 = 0, bx1 = 0, by0 = 0, by1 = 0;
+        if (rel >= 0) {
+            const float *src = gb + (int64_t)(i_lo + rel) * cols;
+            float v[9];
 #pragma unroll
-        for (int j = 0; j < kScanPerThread; ++j) {
-            idx[j] = top - 1 - (j * kThreads + tid);
-#if GGS_BOX_PREFETCH
-            const uint2 box = nbox[j];
-            {
-#else
-            hit[j] = false;
-            bx0[j] = bx1[j] = by0[j] = by1[j] = 0;
-            if (idx[j] >= 0) {
-                const uint2 box = __ldg(boxb + idx[j]);
-#endif
-                bx0[j] = (int)(short)(box.x & 0xffff);
-                bx1[j] = (int)box.x >> 16;
-                by0[j] = (int)(short)(box.y & 0xffff);
-                by1[j] = (int)box.y >> 16;
-                hit[j] = (bx1[j] >= X0) & (bx0[j] <= X1) & (by1[j] >= Y0) & (by0[j] <= Y1);
-            }
-            bal[j] = __ballot_sync(0xffffffffu, hit[j]);
-            if (lane == 0) s_wcnt[j][warp] = __popc(bal[j]);
+            for (int c = 0; c < 9; ++c) v[c] = __ldg(src + c);
+            const Chol ch = kAxes ? encode_axes(v) : load_chol(v);
+            const Decoded d = decode_chol(ch, H, W, k_sigma);
+            uint2 box;
+            make_record(d, r, box);
+            bx0 = (int)(short)(box.x & 0xffff), bx1 = (int)box.x >> 16;
+            by0 = (int)(short)(box.y & 0xffff), by1 = (int)box.y >> 16;
+            hit = (bx1 >= g.X0) & (bx0 <= g.X1) & (by1 >= g.Y0) & (by0 <= g.Y1);
         }
-#if GGS_BOX_PREFETCH
-#pragma unroll
-        for (int j = 0; j < kScanPerThread; ++j) {
-            const int i1 = top - kScanChunk - 1 - (j * kThreads + tid);
-            nbox[j] = (i1 >= 0) ? __ldg(boxb + i1) : make_uint2(0xffff7fffu, 0xffff7fffu);
-        }
-#endif
+        const unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) sm.wcnt[par][0][warp] = __popc(bal);
         __syncthreads();
-        int run = cnt;
+        int pre = 0, tot = 0;
 #pragma unroll
-        for (int j = 0; j < kScanPerThread; ++j) {
-            int pre = 0, tot = 0;
-#pragma unroll
-            for (int w = 0; w < kWarps; ++w) {
-                const int c = s_wcnt[j][w];
-                pre += (w < warp) ? c : 0;
-                tot += c;
-            }
-            if (hit[j]) {
-                const int pos = run + pre + __popc(bal[j] & (lanebit - 1u));
-                const float4 *src = recb + (int64_t)idx[j] * 3;
-                float4 q2 = __ldg(src + 2);
-                q2.y = __uint_as_float(lane_mask(bx0[j], bx1[j], X0));
-                q2.z = __uint_as_float(row_code(by0[j], by1[j], Y0, q2.w < 0.0f));
-                cp_async16(&s_list[pos * 3 + 0], src + 0);  // LDGSTS: no register staging
-                cp_async16(&s_list[pos * 3 + 1], src + 1);
-                s_list[pos * 3 + 2] = q2;
-            }
-            run += tot;
+        for (int w = 0; w < kWarps; ++w) {
+            const int c = sm.wcnt[par][0][w];
+            pre += (w < warp) ? c : 0;
+            tot += c;
         }
-        cnt = run;
-        cp_async_wait_all();
-        __syncthreads();
-        if (cnt > kListCap - kScanChunk || top <= kScanChunk) {
-            if (live) live = composite_list<kStats>(s_list, cnt, lanebit, band_sel, Xf, Ybf, work);
-            cnt = 0;
-            // every band opaque: the rest of the genome is hidden behind what is drawn
-            if (__syncthreads_and(!live)) break;
+        if (hit) {
+            const int e = cnt + pre + __popc(bal & (g.lanebit - 1u));
+            sm.list[e * 3 + 0] = make_float4(r.cx, r.cy, r.A, r.Bq);
+            sm.list[e * 3 + 1] = make_float4(r.Cq, r.la, r.r, r.g);
+            sm.list[e * 3 + 2] = make_float4(r.b, __uint_as_float(lane_mask(bx0, bx1, g.X0)),
+                                             __uint_as_float(row_code(by0, by1, g.Y0, r.h < 0.0f)), r.h);
         }
+        cnt += tot;
+        par ^= 1;
     }
+    __syncthreads();
+    return cnt;
+}
 
-#endif
-
-    // Epilogue: add the background through the remaining transmittance (render.py:236-237),
-    // clamp (render.py:252), optional image store, squared error (fitness.py:16-31).
-    float num = 0.0f, den = 0.0f;
-    const bool want_fit = (target != nullptr);
-    float prr[kPairs][2], pgg[kPairs][2], pbb[kPairs][2], ptt[kPairs][2];
-#define GGS_READ_ALL(k) GGS_PX_READ(k, prr[k], pgg[k], pbb[k], ptt[k])
-    GGS_PAIRS(GGS_READ_ALL)
-#undef GGS_READ_ALL
-#pragma unroll
-    for (int i = 0; i < kRowsPerThread; ++i) {
-        const int Y = Yb + i;
-        const float *pr = prr[i >> 1], *pg = pgg[i >> 1], *pb = pbb[i >> 1], *pt = ptt[i >> 1];
-        if (X < W && Y < H) {
-            const float tr = pt[i & 1];
-            const float cr = clamp01(fmaf(tr, bg_r, pr[i & 1]));
-            const float cg = clamp01(fmaf(tr, bg_g, pg[i & 1]));
-            const float cb = clamp01(fmaf(tr, bg_b, pb[i & 1]));
-            const int64_t p = (int64_t)Y * W + X;
-            if (images != nullptr) {
-                const int64_t at = ((int64_t)b * H * W + p) * 3;
-                if (image_u8) {  // (img * 255).astype(uint8): truncation (utils.py:57)
-                    unsigned char *o = reinterpret_cast<unsigned char *>(images) + at;
-                    o[0] = (unsigned char)(cr * 255.0f);
-                    o[1] = (unsigned char)(cg * 255.0f);
-                    o[2] = (unsigned char)(cb * 255.0f);
-                } else {
-                    float *o = images + at;
-                    o[0] = cr;
-                    o[1] = cg;
-                    o[2] = cb;
-                }
-            }
-            if (want_fit) {
-                const float dr = cr - __ldg(target + 3 * p + 0);
-                const float dg = cg - __ldg(target + 3 * p + 1);
-                const float db = cb - __ldg(target + 3 * p + 2);
-                float w = 1.0f;
-                if (mode == GGS_MODE_MASK)
-                    w = __ldg(mask + p);
-                else if (mode == GGS_MODE_BOOST)
-                    w = 1.0f + beta * clamp01(__ldg(mask + p));
-                num += (dr * dr) * w + (dg * dg) * w + (db * db) * w;
-                den += w;
-            }
+// One finished pixel: background through the remaining transmittance (render.py:236-237), clamp
+// (render.py:252), optional image store, squared error (fitness.py:16-31).
+__device__ __forceinline__ void emit_pixel(const RasterArgs &a, int b, int X, int Y, float pr, float pg,
+                                           float pb, float pt, float &num, float &den)
+{
+    const float cr = clamp01(fmaf(pt, a.bg_r, pr));
+    const float cg = clamp01(fmaf(pt, a.bg_g, pg));
+    const float cb = clamp01(fmaf(pt, a.bg_b, pb));
+    const int64_t p = (int64_t)Y * a.W + X;
+    if (a.images != nullptr) {
+        const int64_t at = ((int64_t)b * a.H * a.W + p) * 3;
+        if (a.image_u8) {  // (img * 255).astype(uint8): truncation (utils.py:57)
+            unsigned char *o = reinterpret_cast<unsigned char *>(a.images) + at;
+            o[0] = (unsigned char)(cr * 255.0f);
+            o[1] = (unsigned char)(cg * 255.0f);
+            o[2] = (unsigned char)(cb * 255.0f);
+        } else {
+            float *o = a.images + at;
+            o[0] = cr;
+            o[1] = cg;
+            o[2] = cb;
         }
     }
-    if (kStats && lane == 0) {
-        // pixel-splat pairs actually evaluated: 64 lanes-rows per blended row pair
-        atomicAdd(stats + 0, (unsigned long long)work[0]);
-        atomicAdd(stats + 1, (unsigned long long)work[1]);
+    if (a.target != nullptr) {
+        const float dr = cr - __ldg(a.target + 3 * p + 0);
+        const float dg = cg - __ldg(a.target + 3 * p + 1);
+        const float db = cb - __ldg(a.target + 3 * p + 2);
+        float w = 1.0f;
+        if (a.mode == GGS_MODE_MASK)
+            w = __ldg(a.mask + p);
+        else if (a.mode == GGS_MODE_BOOST)
+            w = fmaf(a.beta, clamp01(__ldg(a.mask + p)), 1.0f);
+        num += (dr * dr) * w + (dg * dg) * w + (db * db) * w;
+        den += w;
     }
-    if (!want_fit) return;
+}
 
+// Block reduction of (num, den) to this CTA's partial, then the last CTA of the candidate
+// (atomic ticket over its `per_cand` CTAs) combines all partials in index order, in double, and
+// applies the mode formula: fitness is bit-reproducible.
+__device__ __forceinline__ void reduce_and_finish(const RasterArgs &a, int b, int per_cand, float num,
+                                                  float den, RasterSmem &sm, int tid, int lane, int warp)
+{
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         num += __shfl_xor_sync(0xffffffffu, num, o);
         den += __shfl_xor_sync(0xffffffffu, den, o);
     }
     if (lane == 0) {
-        s_red[warp] = num;
-        s_red[kWarps + warp] = den;
+        sm.red[warp] = num;
+        sm.red[kWarps + warp] = den;
     }
     __syncthreads();
     if (tid == 0) {
         float n = 0.0f, d = 0.0f;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
-            n += s_red[w];
-            d += s_red[kWarps + w];
+            n += sm.red[w];
+            d += sm.red[kWarps + w];
         }
-        partial[blockIdx.x] = make_float2(n, d);
+        a.partial[blockIdx.x] = make_float2(n, d);
         __threadfence();
-        const int ticket = atomicAdd(counter + b, 1);
-        s_last = (ticket == ntiles - 1);
+        const int ticket = atomicAdd(a.counter + b, 1);
+        sm.last = (ticket == per_cand - 1);
     }
     __syncthreads();
-    if (s_last && warp == 0) {
-        // Last tile of this candidate: combine the per-tile partials in tile order.
+    if (sm.last && warp == 0) {
         __threadfence();
-        const volatile float2 *pb = partial + (int64_t)b * ntiles;
+        const volatile float2 *pb = a.partial + (int64_t)b * per_cand;
         double n = 0.0, d = 0.0;
-        for (int k = lane; k < ntiles; k += 32) {
+        for (int k = lane; k < per_cand; k += 32) {
             n += (double)pb[k].x;
             d += (double)pb[k].y;
         }
@@ -552,40 +553,183 @@ raster_kernel(const float4 *__restrict__ rec, const uint2 *__restrict__ aabb, in
             d += __shfl_xor_sync(0xffffffffu, d, o);
         }
         if (lane == 0) {
-            const double P = (double)H * (double)W;
+            const double P = (double)a.H * (double)a.W;
             float fit;
-            if (mode == GGS_MODE_PLAIN)
+            if (a.mode == GGS_MODE_PLAIN)
                 fit = (float)(n / (3.0 * P));                            // fitness.py:19
-            else if (mode == GGS_MODE_MASK)
+            else if (a.mode == GGS_MODE_MASK)
                 fit = (float)n / ((float)d + 1e-12f);                    // fitness.py:29-31
             else
                 fit = (float)(n / (3.0 * P)) / ((float)(d / P) + 1e-12f);  // fitness.py:23-27
-            fitness[b] = fit;
-            counter[b] = 0;  // ready for the next launch on this workspace
+            a.fitness[b] = fit;
+            a.counter[b] = 0;  // ready for the next launch on this workspace
+            peer_publish(a.peers, b, fit, (int)(gridDim.x / (unsigned)per_cand));
         }
     }
 }
 
+// Transmittance starts at 1 inside the image and at 0 outside it: pixels beyond the image edge
+// then take no colour and never keep a band from saturating.
+#define GGS_T_INIT(k)                                                        \
+    GGS_PX_INIT(k, (g.X < a.W && g.Yb + 2 * k < a.H) ? 1.0f : 0.0f,          \
+                (g.X < a.W && g.Yb + 2 * k + 1 < a.H) ? 1.0f : 0.0f)
+
+// ---- throughput path: one CTA per (candidate, tile) -------------------------------------------
+template <bool kStats>
+__global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_kernel(const RasterArgs a)
+{
+    unsigned work[2] = {0u, 0u};  // kStats: row pairs blended on the recurrence / exact path
+    __shared__ RasterSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TileGeom g = tile_geometry(blockIdx.x, a.ntx, a.ntiles, lane, warp);
+
+    GGS_PX_DECLARE();
+    GGS_PAIRS(GGS_T_INIT)
+
+    pdl_wait();  // the decode launch ahead of us has completed; nothing above reads memory
+    pdl_trigger();
+    scan_and_composite<kStats>(a.rec + (int64_t)g.b * a.N * 3, a.aabb + (int64_t)g.b * a.N, a.N, g, sm,
+                               tid, lane, warp, work);
+
+    float num = 0.0f, den = 0.0f;
+    float prr[kPairs][2], pgg[kPairs][2], pbb[kPairs][2], ptt[kPairs][2];
+#define GGS_READ_ALL(k) GGS_PX_READ(k, prr[k], pgg[k], pbb[k], ptt[k])
+    GGS_PAIRS(GGS_READ_ALL)
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) {
+        const int Y = g.Yb + i;
+        if (g.X < a.W && Y < a.H)
+            emit_pixel(a, g.b, g.X, Y, prr[i >> 1][i & 1], pgg[i >> 1][i & 1], pbb[i >> 1][i & 1],
+                       ptt[i >> 1][i & 1], num, den);
+    }
+    if (kStats && lane == 0) {
+        // pixel-splat pairs actually evaluated: 64 lanes-rows per blended row pair
+        atomicAdd(a.stats + 0, (unsigned long long)work[0]);
+        atomicAdd(a.stats + 1, (unsigned long long)work[1]);
+    }
+    if (a.target == nullptr) return;
+    reduce_and_finish(a, g.b, a.ntiles, num, den, sm, tid, lane, warp);
+}
+
+// ---- latency path: a cluster of `split` CTAs per (candidate, tile) ----------------------------
+// kDecode: 0 = records from decode_kernel, 1 = fused decode of axes-angle genomes, 2 = fused
+// decode of Cholesky genomes.  blockIdx.x = (candidate * ntiles + tile) * split + k; CTA k owns
+// genome rows [k*S, min(N, (k+1)*S)), S = ceil(N / split); the highest k is the front-most.
+template <int kDecode>
+__global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_split_kernel(const RasterArgs a)
+{
+    unsigned work[2] = {0u, 0u};
+    __shared__ RasterSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = a.split;
+    const int k = (int)(blockIdx.x % (unsigned)K);
+    const TileGeom g = tile_geometry((int)(blockIdx.x / (unsigned)K), a.ntx, a.ntiles, lane, warp);
+    const int S = (a.N + K - 1) / K;
+    const int i_lo = min(k * S, a.N), n = min(a.N, i_lo + S) - i_lo;
+
+    GGS_PX_DECLARE();
+    GGS_PAIRS(GGS_T_INIT)
+
+    pdl_wait();
+    pdl_trigger();
+    if (kDecode == 0) {
+        scan_and_composite<false>(a.rec + ((int64_t)g.b * a.N + i_lo) * 3,
+                                  a.aabb + (int64_t)g.b * a.N + i_lo, n, g, sm, tid, lane, warp, work);
+    } else {
+        const int cnt = build_list_fused<kDecode == 1>(a.genomes + (int64_t)g.b * a.N * a.cols, a.cols,
+                                                       i_lo, n, a.H, a.W, a.k_sigma, g, sm, tid, lane, warp);
+        composite_list<false>(sm.list, cnt, g.lanebit, g.band_sel, g.Xf, g.Ybf, work);
+    }
+
+    // Publish this segment's state: px[row][col] = (r, g, b, t), reusing the list's memory.
+    __syncthreads();  // every warp is done reading the list
+    float4 *px = sm.list;
+    {
+        float prr[kPairs][2], pgg[kPairs][2], pbb[kPairs][2], ptt[kPairs][2];
+        GGS_PAIRS(GGS_READ_ALL)
+#pragma unroll
+        for (int i = 0; i < kRowsPerThread; ++i)
+            px[(warp * kRowsPerThread + i) * kTileW + lane] =
+                make_float4(prr[i >> 1][i & 1], pgg[i >> 1][i & 1], pbb[i >> 1][i & 1], ptt[i >> 1][i & 1]);
+    }
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();
+
+    // Fold the K states front to back for this CTA's share of the tile's rows, then finish
+    // those pixels.  Segment K-1 holds the last splats of the genome: it is the front-most.
+    float num = 0.0f, den = 0.0f;
+    const int rows_per = kTileH / K;
+    for (int p = tid; p < rows_per * kTileW; p += kThreads) {
+        const int row = k * rows_per + p / kTileW, col = p % kTileW;
+        float cr = 0.0f, cgr = 0.0f, cb = 0.0f, t = 1.0f;
+        for (int s = K - 1; s >= 0; --s) {
+            const float4 v = cluster.map_shared_rank(px, s)[row * kTileW + col];
+            cr = fmaf(t, v.x, cr);
+            cgr = fmaf(t, v.y, cgr);
+            cb = fmaf(t, v.z, cb);
+            t *= v.w;
+        }
+        const int X = g.X0 + col, Y = g.Y0 + row;
+        if (X < a.W && Y < a.H) emit_pixel(a, g.b, X, Y, cr, cgr, cb, t, num, den);
+    }
+    cluster.sync();  // nobody leaves while a neighbour still reads its shared memory
+    if (a.target == nullptr) return;
+    reduce_and_finish(a, g.b, a.ntiles * K, num, den, sm, tid, lane, warp);
+}
+#undef GGS_READ_ALL
+#undef GGS_T_INIT
+
 }  // namespace
 
-cudaError_t launch_raster(const Workspace &ws, int B, int N, int H, int W, const float bg[3],
-                          const float *d_target, const float *d_mask, int mode, float beta,
-                          float *d_fitness, void *d_images, int image_u8,
-                          unsigned long long *d_stats, cudaStream_t stream)
+int max_split_for(int N) { return N <= 0 ? 1 : kMaxSplit; }
+
+bool fused_decode_possible(int N, int split)
 {
-    if (B <= 0) return cudaSuccess;
-    const int ntx = tiles_x(W), ntiles = ntx * tiles_y(H);
-    const int64_t grid = (int64_t)B * ntiles;
-    if (grid > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    if (d_stats != nullptr)
-        return launch_kernel(raster_kernel<true>, (unsigned)grid, kThreads, 0, stream, ws.rec, ws.aabb,
-                             N, H, W, ntx, ntiles, bg[0], bg[1], bg[2], d_target, d_mask, mode, beta,
-                             static_cast<float *>(d_images), image_u8, ws.partial, ws.counter,
-                             d_fitness, d_stats);
-    return launch_kernel(raster_kernel<false>, (unsigned)grid, kThreads, 0, stream, ws.rec, ws.aabb, N,
-                         H, W, ntx, ntiles, bg[0], bg[1], bg[2], d_target, d_mask, mode, beta,
-                         static_cast<float *>(d_images), image_u8, ws.partial, ws.counter, d_fitness,
-                         nullptr);
+    return split >= 1 && (N + split - 1) / split <= kListCap;
+}
+
+cudaError_t launch_raster(const RasterLaunch &q, cudaStream_t stream)
+{
+    if (q.B <= 0) return cudaSuccess;
+    const int ntx = tiles_x(q.W), ntiles = ntx * tiles_y(q.H);
+    const int split = q.split < 1 ? 1 : q.split;
+    const int64_t grid = (int64_t)q.B * ntiles * split;
+    if (grid > 0x7fffffffLL || kTileH % split != 0 || split > kMaxSplit) return cudaErrorInvalidConfiguration;
+    RasterArgs a;
+    a.rec = q.ws.rec;
+    a.aabb = q.ws.aabb;
+    a.genomes = q.d_genomes;
+    a.cols = q.cols;
+    a.k_sigma = q.k_sigma;
+    a.N = q.N;
+    a.H = q.H;
+    a.W = q.W;
+    a.ntx = ntx;
+    a.ntiles = ntiles;
+    a.bg_r = q.bg[0];
+    a.bg_g = q.bg[1];
+    a.bg_b = q.bg[2];
+    a.target = q.d_target;
+    a.mask = q.d_mask;
+    a.mode = q.mode;
+    a.beta = q.beta;
+    a.images = static_cast<float *>(q.d_images);
+    a.image_u8 = q.image_u8;
+    a.partial = q.ws.partial;
+    a.counter = q.ws.counter;
+    a.fitness = q.d_fitness;
+    a.stats = q.d_stats;
+    a.split = split;
+    a.peers = q.peers;
+    if (q.fused) {
+        if (!fused_decode_possible(q.N, split)) return cudaErrorInvalidConfiguration;
+        if (q.layout == GGS_LAYOUT_AXES_ANGLE)
+            return launch_kernel_cluster(raster_split_kernel<1>, (unsigned)grid, kThreads, 0, split, stream, a);
+        return launch_kernel_cluster(raster_split_kernel<2>, (unsigned)grid, kThreads, 0, split, stream, a);
+    }
+    if (split > 1) return launch_kernel_cluster(raster_split_kernel<0>, (unsigned)grid, kThreads, 0, split, stream, a);
+    if (q.d_stats != nullptr) return launch_kernel(raster_kernel<true>, (unsigned)grid, kThreads, 0, stream, a);
+    return launch_kernel(raster_kernel<false>, (unsigned)grid, kThreads, 0, stream, a);
 }
 
 }  // namespace ggs

@@ -77,6 +77,7 @@ class ShardedEvaluator:
                  device=None, group=None,
                  evaluate: Optional[Callable[[torch.Tensor], torch.Tensor]] = None):
         self.group = group
+        self._takes_total = False
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.H, self.W, self.k_sigma = int(H), int(W), float(k_sigma)
@@ -86,9 +87,13 @@ class ShardedEvaluator:
             tgt = target.to(dev, torch.float32).contiguous()
             msk = None if weight_mask is None else weight_mask.to(dev, torch.float32).contiguous()
 
-            def evaluate(g: torch.Tensor) -> torch.Tensor:
+            def evaluate(g: torch.Tensor, total: Optional[int] = None) -> torch.Tensor:
+                # the kernel configuration of the WHOLE population, so that the gathered vector
+                # has the bits of a single-GPU evaluation
+                split = evaluator.choose_split(total or g.shape[0], g.shape[1], self.H, self.W)
                 return evaluator.fitness(g, tgt, self.H, self.W, self.k_sigma, weight_mask=msk,
-                                         boost_only=boost_only, device=dev)
+                                         boost_only=boost_only, device=dev, split=split)
+            self._takes_total = True
         self.evaluate = evaluate
 
     # -- fitness -------------------------------------------------------------------------
@@ -114,7 +119,8 @@ class ShardedEvaluator:
             lo, hi = shard_bounds(P, self.world, self.rank)
             assert shard.shape[0] == hi - lo, "shard does not match shard_bounds()"
         if shard.shape[0] > 0:
-            local = self.evaluate(shard.contiguous())
+            local = (self.evaluate(shard.contiguous(), P) if self._takes_total
+                     else self.evaluate(shard.contiguous()))
         else:
             local = torch.empty((0,), dtype=torch.float32, device=population.device)
         if self.world == 1:

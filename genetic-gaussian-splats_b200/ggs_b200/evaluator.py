@@ -123,8 +123,12 @@ def render(genomes: torch.Tensor, H: int, W: int, k_sigma: float = 3.0,
 def fitness(genomes: torch.Tensor, target: torch.Tensor, H: int, W: int, k_sigma: float = 3.0,
             weight_mask: Optional[torch.Tensor] = None, boost_only: bool = False,
             boost_beta: float = 1.0, layout: int = LAYOUT_AXES_ANGLE, want_images: bool = False,
-            device=None):
-    """[B,N,C>=9] genomes -> [B] float32 fitness, fused on device (fitness.py:8-31)."""
+            device=None, split: int = 0):
+    """[B,N,C>=9] genomes -> [B] float32 fitness, fused on device (fitness.py:8-31).
+
+    split: CTAs per (candidate, tile) of the small-batch path, 0 = chosen from B
+    (choose_split).  Pass the split of the WHOLE population when it is evaluated in several
+    calls or on several GPUs and the bits of a single call are wanted."""
     dev = _cuda_device(device if device is not None else genomes.device)
     g = _as_f32(genomes, dev)
     assert g.ndim == 3 and g.shape[2] >= 9
@@ -139,12 +143,22 @@ def fitness(genomes: torch.Tensor, target: torch.Tensor, H: int, W: int, k_sigma
     nbytes = lib().ggs_workspace_bytes(B, N, int(H), int(W))
     with torch.cuda.device(dev):
         ws = _workspace(dev, nbytes)
-        check(lib().ggs_fitness(g.data_ptr(), layout, B, N, C, int(H), int(W), float(k_sigma),
-                                t.data_ptr(), None if m is None else m.data_ptr(),
-                                mode_of(m, boost_only), float(boost_beta), fit.data_ptr(),
-                                None if img is None else img.data_ptr(), ws.data_ptr(),
-                                ws.numel(), _stream_ptr(dev)), "ggs_fitness")
+        check(lib().ggs_fitness_ex(g.data_ptr(), layout, B, N, C, int(H), int(W), float(k_sigma),
+                                   t.data_ptr(), None if m is None else m.data_ptr(),
+                                   mode_of(m, boost_only), float(boost_beta), fit.data_ptr(),
+                                   None if img is None else img.data_ptr(), ws.data_ptr(),
+                                   ws.numel(), int(split), _stream_ptr(dev)), "ggs_fitness")
     return (fit, img) if want_images else fit
+
+
+def choose_split(B: int, N: int, H: int, W: int) -> int:
+    """The split (1, 2, 4 or 8 CTAs per tile) the library picks for a batch of B candidates."""
+    return int(lib().ggs_choose_split(int(B), int(N), int(H), int(W)))
+
+
+def set_option(name: str, value: int) -> None:
+    """Process-wide switch of the library: "pdl", "split", "fuse" (ggs_set_option)."""
+    check(lib().ggs_set_option(name.encode(), int(value)), "ggs_set_option")
 
 
 def probe_peaks() -> dict:

@@ -35,6 +35,10 @@ SIGNATURES = {
     "ggs_render_u8": (_i, [_vp, _i, _i, _i, _i, _i, _i, _f, ctypes.POINTER(_f), _vp, _vp, _sz, _vp]),
     "ggs_fitness": (_i, [_vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz,
                          _vp]),
+    "ggs_fitness_ex": (_i, [_vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _i, _f, _vp, _vp, _vp, _sz,
+                            _i, _vp]),
+    "ggs_choose_split": (_i, [_i, _i, _i, _i]),
+    "ggs_set_option": (_i, [ctypes.c_char_p, _i]),
     "ggs_ctx_create": (_i, [_i, ctypes.POINTER(_vp)]),
     "ggs_ctx_destroy": (None, [_vp]),
     "ggs_ctx_set_target": (_i, [_vp, _vp, _vp, _i, _i]),

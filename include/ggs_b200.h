@@ -63,7 +63,8 @@ int ggs_device_count(void);
  * Device scratch needed by ggs_render / ggs_fitness for a batch of B candidates of N
  * splats on an H x W image: decoded splat records, packed AABBs, per-tile partial sums
  * and per-candidate completion counters.  The caller owns the buffer (e.g. a torch
- * uint8 tensor) and may reuse it across calls on the same stream.
+ * uint8 tensor) and may reuse it across calls on the same stream.  It need not be
+ * initialised.
  */
 size_t ggs_workspace_bytes(int B, int N, int H, int W);
 
@@ -110,13 +111,41 @@ int ggs_render_u8(const float *d_genomes, int layout, int B, int N, int cols, in
  * d_target: [H][W][3] in [0,1]; d_mask: [H][W] or NULL (required unless GGS_MODE_PLAIN);
  * d_fitness: [B] (lower is better); d_images: [B][H][W][3] or NULL.
  * Background is white as in the reference (render.py:209).  The per-candidate
- * reduction order is fixed, so results are bit-reproducible run to run and
- * independent of how a population is split into calls.
+ * reduction order is fixed, so results are bit-reproducible run to run and, for a given
+ * `split` (see ggs_fitness_ex below), independent of how a population is split into calls.
  */
 int ggs_fitness(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
                 float k_sigma, const float *d_target, const float *d_mask, int mode,
                 float boost_beta, float *d_fitness, float *d_images, void *d_workspace,
                 size_t workspace_bytes, void *stream);
+
+/*
+ * Small batches (simulated annealing's neighbours, a 32-individual GA, single frames).  One CTA
+ * per (candidate, 32x32 tile) leaves most of a B200 idle when B * tiles is a few hundred, so the
+ * library can give a tile to a thread-block cluster of `split` = 2, 4 or 8 CTAs: CTA k composites
+ * the k-th segment of the genome and the partial (colour, transmittance) states are folded in
+ * genome order through distributed shared memory ("over" is associative); when a segment fits the
+ * CTA's splat list the decode is fused into the same launch, so an evaluation is ONE kernel.
+ * Every entry point picks `split` from B (ggs_choose_split: the largest split that keeps the grid
+ * within one wave).  The fold changes the floating-point association, so results for different
+ * `split` agree to ~1e-7 but not bit for bit: a caller that evaluates ONE population in several
+ * calls or on several GPUs and wants the bits of a single call passes the split of the whole
+ * population explicitly (ggs_fitness_ex; ggs_ctx_fitness_host and the engines do).
+ */
+int ggs_choose_split(int B, int N, int H, int W);
+/* ggs_fitness with an explicit split: 0 = ggs_choose_split(B, ...), else 1, 2, 4 or 8. */
+int ggs_fitness_ex(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,
+                   float k_sigma, const float *d_target, const float *d_mask, int mode,
+                   float boost_beta, float *d_fitness, float *d_images, void *d_workspace,
+                   size_t workspace_bytes, int split, void *stream);
+/*
+ * Process-wide switches, for A/B timing and tests; the defaults come from the environment
+ * variables read at first use.  "pdl" (GGS_B200_PDL, default 1): programmatic dependent launch
+ * between the kernels of a step.  "split" (GGS_B200_SPLIT, default 0 = automatic): force 1, 2, 4
+ * or 8 wherever the caller does not pass one.  "fuse" (GGS_B200_FUSE, default -1 = when the grid
+ * is a single wave): 0 never / 1 whenever a segment fits, decode inside the raster launch.
+ */
+int ggs_set_option(const char *name, int value);
 
 /* ---- host-buffer path (fitness_population, modules/fitness.py:35-48) ------------- */
 

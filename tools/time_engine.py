@@ -1,12 +1,13 @@
 #!/usr/bin/env python
 """Device time per GA generation / SA iteration on the engines (ggs_ga_run / ggs_sa_run), CUDA
 events around a block of enqueued steps, with programmatic dependent launch on and off
-(GGS_B200_PDL is read at every launch, so both run in one process on the same state)."""
+(ggs_set_option("pdl", ...) switches it, so both run in one process on the same state)."""
 import math, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "genetic-gaussian-splats_b200")]
 import numpy as np
 import torch
+import ggs_b200
 import modules.config as C
 from ggs_b200 import synth
 from ggs_b200.engine import GaEngine, SaEngine
@@ -34,7 +35,7 @@ def ga(side, N, P, steps):
         eng.run(rows, C.TOUR_K, C.CXPB, C.MUTPB, lo, hi); return steps
     out = {}
     for pdl in ("1", "0", "1", "0"):
-        os.environ["GGS_B200_PDL"] = pdl
+        ggs_b200.set_option("pdl", int(pdl))
         out.setdefault(pdl, []).append(events(block, 2))
     eng.close()
     print(f"GA  {side}x{side}, {N} splats, population {P}: {min(out['1']):9.1f} us/generation with PDL, "
@@ -54,7 +55,7 @@ def sa(side, N, tries, steps):
         eng.run(rows, [1e-4] * steps, uni, C.MUTPB, lo, hi); return steps
     out = {}
     for pdl in ("1", "0", "1", "0"):
-        os.environ["GGS_B200_PDL"] = pdl
+        ggs_b200.set_option("pdl", int(pdl))
         out.setdefault(pdl, []).append(events(block, 2))
     eng.close()
     print(f"SA  {side}x{side}, {N} splats, {tries} tries: {min(out['1']):9.1f} us/iteration with PDL, "

@@ -1,27 +1,52 @@
 #!/usr/bin/env python
-"""Latency of the fitness entry points at small batch (the SA regime, BASELINE config 2)."""
-import os, sys, time
+"""Latency of one evaluation at small batch (BASELINE configs 1 and 2, the SA regime) for every
+split / fusion variant of the raster: device time per call from CUDA events around a run of
+back-to-back calls.  Prints one line per (shape, split, fuse) and the automatic choice."""
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "genetic-gaussian-splats_b200")]
 import torch
 import ggs_b200
 from ggs_b200 import synth
-from modules.fitness import fitness_many, fitness_population
-H = W = 256; N = 500
-t_np = synth.synthetic_target_np(H, W, 0)
-target = torch.from_numpy(t_np).cuda(); mask = torch.from_numpy(synth.importance_mask_np(t_np)).cuda()
-for B in (1, 8, 64):
-    g = torch.from_numpy(synth.new_population_np(B, N, H, W, seed=1)).cuda()
-    pop = list(g.unbind(0))
-    def t(fn, n=300):
-        for _ in range(20): fn()
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        for _ in range(n): fn()
-        torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e6
+
+SHAPES = [("config 1: 128x128, 100 splats, P 32", 128, 100, 32),
+          ("config 2: 256x256, 500 splats, 8 neighbours", 256, 500, 8),
+          ("256x256, 500 splats, 1 candidate (sequential SA try)", 256, 500, 1),
+          ("256x256, 512 splats, 24 children (reference default GA)", 256, 512, 24),
+          ("512x512, 4000 splats, 1 candidate (final frame)", 512, 4000, 1)]
+
+
+def device_us(fn, n=200):
+    for _ in range(20):
+        fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
     e0.record()
-    for _ in range(100): ggs_b200.fitness(g, target, H, W, 3.0, weight_mask=mask)
-    e1.record(); torch.cuda.synchronize()
-    print(f"B={B:3d}: device time/call {e0.elapsed_time(e1)*10:.1f} us | async fitness(tensor) {t(lambda: ggs_b200.fitness(g, target, H, W, 3.0, weight_mask=mask)):.1f} us | "
-          f"fitness_many(list) {t(lambda: fitness_many(pop, target, H, W, 3.0, 'cuda', weight_mask=mask)):.1f} us | "
-          f"fitness_population(list)->floats {t(lambda: fitness_population(pop, target, H, W, 3.0, 'cuda', weight_mask=mask)):.1f} us")
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / n
+
+
+for name, side, N, B in SHAPES:
+    H = W = side
+    t_np = synth.synthetic_target_np(H, W, 0)
+    target = torch.from_numpy(t_np).cuda()
+    mask = torch.from_numpy(synth.importance_mask_np(t_np)).cuda()
+    g = torch.from_numpy(synth.new_population_np(B, N, H, W, seed=1)).cuda()
+    auto = ggs_b200.choose_split(B, N, H, W)
+    print(f"{name}: automatic split {auto}")
+    for split in (1, 2, 4, 8):
+        row = []
+        for fuse in (0, 1):
+            ggs_b200.set_option("fuse", fuse)
+            try:
+                us = device_us(lambda: ggs_b200.fitness(g, target, H, W, 3.0, weight_mask=mask, split=split))
+                row.append(f"{'fused' if fuse else 'decode+raster'} {us:7.1f} us")
+            except ggs_b200.GgsError as e:
+                row.append(f"{'fused' if fuse else 'decode+raster'}   n/a")
+        print(f"   split {split}: " + " | ".join(row))
+    ggs_b200.set_option("fuse", -1)
+    us = device_us(lambda: ggs_b200.fitness(g, target, H, W, 3.0, weight_mask=mask))
+    print(f"   default entry: {us:7.1f} us per evaluation, {B / us * 1e6:,.0f} candidates/s")
