@@ -32,6 +32,7 @@ SOURCES = {
     "ggs_breed.cu": [],
     "ggs_mask.cu": ["-fmad=false"],   # one rounding per operation, like the reference's torch ops
     "ggs_engine.cu": [],
+    "ggs_peers.cu": [],
     "ggs_probe.cu": [],
     "ggs_api.cu": [],
 }

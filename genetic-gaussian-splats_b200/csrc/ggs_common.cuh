@@ -129,6 +129,21 @@ cudaError_t launch_importance_mask(const float *d_image, int H0, int W0, int H, 
 // probe.cu
 cudaError_t probe_peaks(float *h_out5);
 
+// peers.cu: the P2P fitness exchange between the GPUs of a box (struct ggs_peers is the C ABI's)
+}  // namespace ggs
+struct ggs_peers;
+namespace ggs {
+int peers_rank(const ggs_peers *p);
+int peers_world(const ggs_peers *p);
+int peers_capacity(const ggs_peers *p);
+bool peers_ready(const ggs_peers *p);
+PeerStores peers_next(ggs_peers *p, int offset);   // takes the next epoch number
+unsigned *peers_flags(ggs_peers *p);               // this rank's arrival flags [world]
+int *peers_status(ggs_peers *p);
+float *peers_gathered(ggs_peers *p, unsigned epoch);  // this rank's gathered vector of that epoch
+cudaError_t peers_signal_empty(const PeerStores &s, cudaStream_t st);
+cudaError_t peers_wait(ggs_peers *p, unsigned epoch, cudaStream_t st);
+
 void set_error(const char *fmt, ...);
 
 // ---- programmatic dependent launch (PDL) --------------------------------------------------
@@ -158,6 +173,38 @@ __device__ __forceinline__ void peer_publish(const PeerStores &p, int b, float f
         __threadfence_system();
         for (int r = 0; r < p.n; ++r)
             asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flag[r] + p.rank), "r"(p.epoch) : "memory");
+    }
+}
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Thread r < world waits until sender r's arrival flag has reached `epoch` (the values that
+// sender published before it are then visible).  A sender that never arrives -- a rank died --
+// would spin for ever: give up after 20 s and leave a mark the host reads (ggs_peers_status).
+__device__ __forceinline__ void peer_wait(const unsigned *flags, int world, unsigned epoch, int *status)
+{
+    const int r = threadIdx.x;
+    if (r < world) {
+        const unsigned long long t0 = global_ns();
+        while ((int)(ld_acquire_sys(flags + r) - epoch) < 0) {
+            if (global_ns() - t0 > 20ull * 1000 * 1000 * 1000) {
+                *status = 1;
+                break;
+            }
+            __nanosleep(64);
+        }
     }
 }
 

@@ -75,6 +75,11 @@ struct SelectParams {
     double *best_fit;        // in / out
     int *no_improve;         // in / out
     int P, N, n_elite;
+    // sharded evaluation: child_fit is this rank's gathered vector; wait for every rank's values
+    const unsigned *wait_flags;
+    int *wait_status;
+    int wait_world;
+    unsigned wait_epoch;
 };
 
 // Grid = 1 + n_elite CTAs.  CTA e + 1 copies elite e (the e-th best of the current generation,
@@ -96,8 +101,12 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams q)
         copy_row(q.next + e * row, q.pop + q.order_in[e] * row, row, tid, kSelectThreads);
         return;
     }
+    if (q.wait_world > 0) {  // the children's fitness arrives from the other GPUs (ggs_peers.cu)
+        peer_wait(q.wait_flags, q.wait_world, q.wait_epoch, q.wait_status);
+        __syncthreads();
+    }
     for (int e = tid; e < q.n_elite; e += kSelectThreads) q.new_fit[e] = q.fit[q.order_in[e]];
-    for (int i = tid; i < keep; i += kSelectThreads) q.new_fit[q.n_elite + i] = q.child_fit[i];
+    for (int i = tid; i < keep; i += kSelectThreads) q.new_fit[q.n_elite + i] = __ldcv(q.child_fit + i);
     __syncthreads();
 
     // stable ascending ranking: the index in the low word makes every key distinct
@@ -258,9 +267,51 @@ struct ggs_ga {
     int cur = 0;          // buffer holding the current population
     int generation = -1;  // generations completed; -1 until ggs_ga_start
     bool has_target = false;
+    ggs_peers *peers = nullptr;  // evaluation sharded over the ranks of this group, or NULL
 };
 
-static int ga_rank(ggs_ga *g, int n_elite, int next_buf, cudaStream_t st)
+// Contiguous split of `total` items; the first total % world ranks get one more (the rule of
+// ggs_b200.distributed.shard_bounds).
+static void shard_bounds(int total, int world, int rank, int *lo, int *hi)
+{
+    const int base = total / world, extra = total % world;
+    *lo = rank * base + (rank < extra ? rank : extra);
+    *hi = *lo + base + (rank < extra ? 1 : 0);
+}
+
+// Fitness of `count` individuals starting at `first` -> fit_out[count] (g->child_fit on one GPU).
+// Sharded: this rank evaluates its slice with the configuration of the whole batch and every
+// rank's values land in the gathered vector of a new epoch, returned through *fit_out / *epoch;
+// the consumer (select_kernel) waits for the flags.
+static int ga_evaluate(ggs_ga *g, const float *first, int count, const float **fit_out, unsigned *epoch,
+                       cudaStream_t st)
+{
+    const float bg[3] = {1.0f, 1.0f, 1.0f};
+    const float *mask = g->mode == GGS_MODE_PLAIN ? nullptr : g->mask;
+    EvalOptions opt = owned_workspace();
+    *epoch = 0;
+    if (g->peers == nullptr) {
+        *fit_out = g->child_fit;
+        return evaluate(first, GGS_LAYOUT_AXES_ANGLE, count, g->N, 9, g->H, g->W, g->k_sigma, bg, g->target,
+                        mask, g->mode, g->beta, g->child_fit, nullptr, 0, g->ws, g->ws_bytes, st, opt);
+    }
+    int lo = 0, hi = 0;
+    shard_bounds(count, peers_world(g->peers), peers_rank(g->peers), &lo, &hi);
+    opt.split = choose_split(count, g->N, g->H, g->W);
+    opt.peers = peers_next(g->peers, lo);
+    *epoch = opt.peers.epoch;
+    float *mine = peers_gathered(g->peers, opt.peers.epoch);
+    *fit_out = mine;
+    if (hi > lo)
+        return evaluate(first + (size_t)lo * g->N * 9, GGS_LAYOUT_AXES_ANGLE, hi - lo, g->N, 9, g->H, g->W,
+                        g->k_sigma, bg, g->target, mask, g->mode, g->beta, mine + lo, nullptr, 0, g->ws,
+                        g->ws_bytes, st, opt);
+    GGS_TRY(peers_signal_empty(opt.peers, st));
+    return GGS_OK;
+}
+
+static int ga_rank(ggs_ga *g, int n_elite, int next_buf, const float *child_fit, unsigned epoch,
+                   cudaStream_t st)
 {
     SelectParams q;
     q.pop = g->room[g->cur];
@@ -268,8 +319,12 @@ static int ga_rank(ggs_ga *g, int n_elite, int next_buf, cudaStream_t st)
     q.order_in = g->order[g->ord];
     q.order_out = g->order[g->ord ^ 1];
     q.next = g->room[next_buf];
-    q.child_fit = g->child_fit;
+    q.child_fit = child_fit;
     q.new_fit = g->fit[next_buf];
+    q.wait_world = (g->peers != nullptr && epoch != 0) ? peers_world(g->peers) : 0;
+    q.wait_flags = q.wait_world ? peers_flags(g->peers) : nullptr;
+    q.wait_status = q.wait_world ? peers_status(g->peers) : nullptr;
+    q.wait_epoch = epoch;
     q.curve = g->curves + (size_t)(g->generation + 1) * 3;
     q.best_ind = g->best_ind;
     q.best_fit = g->best_fit;
@@ -404,10 +459,9 @@ int ggs_ga_start(ggs_ga *g, const float *d_population, int cols, uint64_t seed, 
     // generation 0: the given population (first 9 columns), evaluated and ranked
     GGS_TRY(cudaMemcpy2DAsync(g->room[0], 9 * sizeof(float), d_population, (size_t)cols * sizeof(float),
                               9 * sizeof(float), (size_t)g->P * g->N, cudaMemcpyDeviceToDevice, st));
-    const float bg[3] = {1.0f, 1.0f, 1.0f};
-    int rc = evaluate(g->room[0], GGS_LAYOUT_AXES_ANGLE, g->P, g->N, 9, g->H, g->W, g->k_sigma, bg,
-                      g->target, g->mode == GGS_MODE_PLAIN ? nullptr : g->mask, g->mode, g->beta,
-                      g->child_fit, nullptr, 0, g->ws, g->ws_bytes, st, owned_workspace());
+    const float *fit = nullptr;
+    unsigned epoch = 0;
+    int rc = ga_evaluate(g, g->room[0], g->P, &fit, &epoch, st);
     if (rc) return rc;
     const double inf = INFINITY;
     const int zero = 0;
@@ -416,7 +470,7 @@ int ggs_ga_start(ggs_ga *g, const float *d_population, int cols, uint64_t seed, 
     g->seed = seed;
     g->cur = 0;
     g->generation = -1;
-    rc = ga_rank(g, 0, 0, st);  // no elites: new_fit = child_fit, rows already in place
+    rc = ga_rank(g, 0, 0, fit, epoch, st);  // no elites: new_fit = child_fit, rows already in place
     if (rc) return rc;
     g->generation = 0;
     return GGS_OK;
@@ -440,7 +494,6 @@ int ggs_ga_run(ggs_ga *g, int count, const float *h_sigma6, int tour_k, float cx
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GGS_TRY(cudaSetDevice(g->device));
-    const float bg[3] = {1.0f, 1.0f, 1.0f};
     const int keep = g->P - g->n_elite;
     const size_t row = (size_t)g->N * 9;
     for (int k = 0; k < count; ++k) {
@@ -449,11 +502,11 @@ int ggs_ga_run(ggs_ga *g, int count, const float *h_sigma6, int tour_k, float cx
         GGS_TRY(launch_breed(g->room[g->cur], g->fit[g->cur], g->P, g->N, 9, keep, children, tour_k,
                              cxpb, mutpb, h_sigma6 + 6 * (size_t)k, log_scale_lo, log_scale_hi,
                              g->seed, (uint32_t)gen, st));
-        int rc = evaluate(children, GGS_LAYOUT_AXES_ANGLE, keep, g->N, 9, g->H, g->W, g->k_sigma, bg,
-                          g->target, g->mode == GGS_MODE_PLAIN ? nullptr : g->mask, g->mode,
-                          g->beta, g->child_fit, nullptr, 0, g->ws, g->ws_bytes, st, owned_workspace());
+        const float *fit = nullptr;
+        unsigned epoch = 0;
+        int rc = ga_evaluate(g, children, keep, &fit, &epoch, st);
         if (rc) return rc;
-        rc = ga_rank(g, g->n_elite, nb, st);
+        rc = ga_rank(g, g->n_elite, nb, fit, epoch, st);
         if (rc) return rc;
         g->cur = nb;
         g->generation = gen;
@@ -487,6 +540,24 @@ int ggs_ga_state(ggs_ga *g, void *stream, int *h_generation, double *h_best_fitn
                                 cudaMemcpyDeviceToHost, st));
     GGS_TRY(cudaStreamSynchronize(st));
     if (h_generation) *h_generation = g->generation;
+    return GGS_OK;
+}
+
+int ggs_ga_set_peers(ggs_ga *g, ggs_peers *peers)
+{
+    if (!g) {
+        set_error("ggs_ga_set_peers: NULL engine");
+        return GGS_EINVAL;
+    }
+    if (g->generation >= 0) {
+        set_error("ggs_ga_set_peers: call before ggs_ga_start");
+        return GGS_EINVAL;
+    }
+    if (peers != nullptr && (!peers_ready(peers) || peers_capacity(peers) < g->P)) {
+        set_error("ggs_ga_set_peers: peers not connected, or their capacity is below the population (%d)", g->P);
+        return GGS_EINVAL;
+    }
+    g->peers = (peers != nullptr && peers_world(peers) > 1) ? peers : nullptr;
     return GGS_OK;
 }
 

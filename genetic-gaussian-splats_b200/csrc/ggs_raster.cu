@@ -211,8 +211,11 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
                                                unsigned lanebit, unsigned band_sel, float Xf,
                                                float Ybf, unsigned (&work)[2])
 {
-    for (int s = 0; s < cnt; ++s) {
-        const float4 q2 = list[3 * s + 2];
+    // the entry pointer advances by hand: with list[3 * s + k] ptxas of this build rebuilt the
+    // address from the (uniform) counter with two FMA-pipe IMADs per entry
+    const float4 *q = list;
+    for (int s = 0; s < cnt; ++s, q += 3) {
+        const float4 q2 = q[2];
         if ((s & (kSatEvery - 1)) == kSatEvery - 1) {
             float tmax = 0.0f;
 #define GGS_TMAX(k)                        \
@@ -227,8 +230,8 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
         }
         const unsigned c = __byte_perm(__float_as_uint(q2.z), 0u, band_sel);  // this band's byte
         if (c == kBandMiss) continue;  // warp-uniform
-        const float4 q0 = list[3 * s + 0];
-        const float4 q1 = list[3 * s + 1];
+        const float4 q0 = q[0];
+        const float4 q1 = q[1];
         const bool in_x = (__float_as_uint(q2.y) & lanebit) != 0u;
         const float qx = Xf - q0.x;
         const float t1 = q0.w * qx;                       // Bq*qx
@@ -330,15 +333,25 @@ __device__ __forceinline__ TileGeom tile_geometry(int cand_tile, int ntx, int nt
     return g;
 }
 
-// Shared memory of a CTA (static, 29 KB): the staged list, the index list of the scan, the
-// per-warp hit counts of two rounds, the fitness reduction scratch.
-struct __align__(16) RasterSmem {
-    float4 list[kListCap * 3];
-    int idx[kListCap];
-    int wcnt[2][kScanPerThread][kWarps];
-    float red[2 * kWarps];
-    int last;
+// Shared memory of a CTA (static, 26 KB): the staged list, the index list of the scan, the
+// per-warp hit counts of two rounds, the fitness reduction scratch.  The arrays are declared one
+// by one in the kernels (GGS_SMEM_DECLARE) and handed to the helpers as pointers: as members of
+// one struct ptxas stopped keeping the composite loop's counter and list address in uniform
+// registers (17 uniform-datapath operations per list entry became vector ones: 7 % slower).
+struct RasterSmem {
+    float4 *list;                          // [kListCap * 3]
+    int *idx;                              // [kListCap]
+    int (*wcnt)[kScanPerThread][kWarps];   // [2]
+    float *red;                            // [2 * kWarps]
+    int *last_;
 };
+#define GGS_SMEM_DECLARE()                                   \
+    __shared__ float4 s_list[kListCap * 3];                  \
+    __shared__ int s_wcnt[2][kScanPerThread][kWarps];        \
+    __shared__ int s_idx[kListCap];                          \
+    __shared__ float s_red[2 * kWarps];                      \
+    __shared__ int s_last;                                   \
+    const RasterSmem sm = {s_list, s_idx, s_wcnt, s_red, &s_last}
 
 // Walk records [0, n) of `recb` / `boxb` from the last to the first (front to back) and blend
 // the ones that touch the tile.  Slot j of a round maps thread `tid` to record
@@ -350,7 +363,7 @@ struct __align__(16) RasterSmem {
 template <bool kStats>
 __device__ __forceinline__ void scan_and_composite(const float4 *__restrict__ recb,
                                                    const uint2 *__restrict__ boxb, int n,
-                                                   const TileGeom &g, RasterSmem &sm, int tid, int lane,
+                                                   const TileGeom &g, const RasterSmem &sm, int tid, int lane,
                                                    int warp, unsigned (&work)[2])
 {
     bool live = true;  // warp-uniform: this band still has a non-opaque pixel
@@ -428,7 +441,7 @@ __device__ __forceinline__ void scan_and_composite(const float4 *__restrict__ re
 template <bool kAxes>
 __device__ __forceinline__ int build_list_fused(const float *__restrict__ gb, int cols, int i_lo, int n,
                                                 int H, int W, float k_sigma, const TileGeom &g,
-                                                RasterSmem &sm, int tid, int lane, int warp)
+                                                const RasterSmem &sm, int tid, int lane, int warp)
 {
     int cnt = 0, par = 0;
     for (int top = n; top > 0; top -= kThreads) {
@@ -512,9 +525,11 @@ __device__ __forceinline__ void emit_pixel(const RasterArgs &a, int b, int X, in
 
 // Block reduction of (num, den) to this CTA's partial, then the last CTA of the candidate
 // (atomic ticket over its `per_cand` CTAs) combines all partials in index order, in double, and
-// applies the mode formula: fitness is bit-reproducible.
-__device__ __forceinline__ void reduce_and_finish(const RasterArgs &a, int b, int per_cand, float num,
-                                                  float den, RasterSmem &sm, int tid, int lane, int warp)
+// applies the mode formula: fitness is bit-reproducible.  Deliberately NOT inlined: it runs once
+// per CTA, and with its body (and the peer stores) inside the kernel ptxas moved the composite
+// loop's list address out of the uniform registers.
+__device__ __noinline__ void reduce_and_finish(const RasterArgs &a, int b, int per_cand, float num,
+                                                  float den, const RasterSmem &sm, int tid, int lane, int warp)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -536,10 +551,10 @@ __device__ __forceinline__ void reduce_and_finish(const RasterArgs &a, int b, in
         a.partial[blockIdx.x] = make_float2(n, d);
         __threadfence();
         const int ticket = atomicAdd(a.counter + b, 1);
-        sm.last = (ticket == per_cand - 1);
+        *sm.last_ = (ticket == per_cand - 1);
     }
     __syncthreads();
-    if (sm.last && warp == 0) {
+    if (*sm.last_ && warp == 0) {
         __threadfence();
         const volatile float2 *pb = a.partial + (int64_t)b * per_cand;
         double n = 0.0, d = 0.0;
@@ -576,10 +591,10 @@ __device__ __forceinline__ void reduce_and_finish(const RasterArgs &a, int b, in
 
 // ---- throughput path: one CTA per (candidate, tile) -------------------------------------------
 template <bool kStats>
-__global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_kernel(const RasterArgs a)
+__global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_kernel(const __grid_constant__ RasterArgs a)
 {
     unsigned work[2] = {0u, 0u};  // kStats: row pairs blended on the recurrence / exact path
-    __shared__ RasterSmem sm;
+    GGS_SMEM_DECLARE();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const TileGeom g = tile_geometry(blockIdx.x, a.ntx, a.ntiles, lane, warp);
 
@@ -616,10 +631,10 @@ __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_kernel(const 
 // decode of Cholesky genomes.  blockIdx.x = (candidate * ntiles + tile) * split + k; CTA k owns
 // genome rows [k*S, min(N, (k+1)*S)), S = ceil(N / split); the highest k is the front-most.
 template <int kDecode>
-__global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_split_kernel(const RasterArgs a)
+__global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_split_kernel(const __grid_constant__ RasterArgs a)
 {
     unsigned work[2] = {0u, 0u};
-    __shared__ RasterSmem sm;
+    GGS_SMEM_DECLARE();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = a.split;
     const int k = (int)(blockIdx.x % (unsigned)K);

@@ -62,6 +62,15 @@ SIGNATURES = {
                         _f, _vp]),
     "ggs_sa_state": (_i, [_vp, _vp, ctypes.POINTER(_i), ctypes.POINTER(_d), ctypes.POINTER(_d), _vp,
                           _i, _vp, _vp]),
+    "ggs_peers_create": (_i, [_i, _i, _i, _i, ctypes.POINTER(_vp)]),
+    "ggs_peers_destroy": (None, [_vp]),
+    "ggs_peers_export": (_i, [_vp, _vp]),
+    "ggs_peers_connect": (_i, [_vp, _vp]),
+    "ggs_peers_connect_local": (_i, [_vp, ctypes.POINTER(_vp)]),
+    "ggs_peers_status": (_i, [_vp, _vp]),
+    "ggs_fitness_allgather": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp, _vp, _i, _f, _i, _i, _vp,
+                                   _sz, ctypes.POINTER(_vp), _vp]),
+    "ggs_ga_set_peers": (_i, [_vp, _vp]),
     "ggs_mask_workspace_bytes": (_sz, [_i, _i]),
     "ggs_importance_mask": (_i, [_vp, _i, _i, _i, _i, _i, ctypes.POINTER(_i), _i, _d, _d, _d, _d, _i,
                                  _d, _vp, _vp, _sz, _vp]),

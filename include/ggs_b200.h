@@ -263,6 +263,52 @@ int ggs_sa_state(ggs_sa *sa, void *stream, int *h_iteration, double *h_best_ener
                  double *h_current_energy, double *h_curves2, int curves_from, float *h_best_state,
                  float *h_current_state);
 
+/* ---- the population sharded over the GPUs of one box ----------------- */
+
+/*
+ * The fitness all-gather without a collective launch.  One process per GPU; every rank creates a
+ * ggs_peers on its device, exports a CUDA IPC handle of its receive buffer, the handles are
+ * exchanged by the host (torch.distributed, MPI, a file: 64 bytes per rank) and mapped with
+ * ggs_peers_connect.  After that the raster kernel itself delivers: the CTA that finishes a
+ * candidate stores its fitness into EVERY rank's gathered vector over NVLink, and the launch's
+ * last candidate raises a flag on every rank (system-scope release); consumers wait for `world`
+ * flags.  All ranks must issue the same sequence of gathers (epochs advance in lockstep); the
+ * gathered vector of a call stays valid until the call after the next one.
+ * capacity: largest population (floats in the gathered vector); world <= 8.
+ */
+typedef struct ggs_peers ggs_peers;
+#define GGS_IPC_HANDLE_BYTES 64
+int ggs_peers_create(int device, int rank, int world, int capacity, ggs_peers **out);
+void ggs_peers_destroy(ggs_peers *peers);
+int ggs_peers_export(ggs_peers *peers, void *h_handle /* GGS_IPC_HANDLE_BYTES */);
+int ggs_peers_connect(ggs_peers *peers, const void *h_handles /* world x GGS_IPC_HANDLE_BYTES, by rank */);
+/* Ranks that live in ONE process (one thread or process driving several GPUs, or several groups
+ * on one GPU): connect through the objects themselves instead of IPC handles.  all[r] = rank r. */
+int ggs_peers_connect_local(ggs_peers *peers, ggs_peers *const *all);
+/* Synchronises `stream`; GGS_ECUDA if a wait for a peer's values timed out (a rank died). */
+int ggs_peers_status(ggs_peers *peers, void *stream);
+/*
+ * fitness_many of this rank's shard -- candidates [offset, offset + B) of a population of `total`
+ * -- with the result delivered to every rank: enqueues the evaluation (kernel configuration of
+ * the WHOLE population, so the gathered vector has the bits of a single-GPU evaluation) and a
+ * one-warp wait for the other ranks' values.  *d_gathered: this rank's copy of the whole
+ * vector [total], valid in stream order after this call.  B may be 0 (an empty shard).
+ */
+int ggs_fitness_allgather(ggs_peers *peers, const float *d_genomes, int layout, int B, int N,
+                          int cols, int H, int W, float k_sigma, const float *d_target,
+                          const float *d_mask, int mode, float boost_beta, int offset, int total,
+                          void *d_workspace, size_t workspace_bytes, const float **d_gathered,
+                          void *stream);
+/*
+ * Shards the evaluation of a GA engine over the ranks of `peers` (or NULL: back to one GPU).
+ * Every rank runs the same engine calls on the same starting population and seed: breeding,
+ * elitism and ranking are replicated (deterministic counter-based streams), rank r evaluates its
+ * contiguous slice of the children and the fitness values travel as above -- the select kernel
+ * waits for the flags itself, so a generation is still four launches and no host sync.  Call
+ * before ggs_ga_start.  The result is bit-identical to the single-GPU engine.
+ */
+int ggs_ga_set_peers(ggs_ga *ga, ggs_peers *peers);
+
 /* ---- importance mask, the weight_mask input of the fitness ---- */
 
 /*

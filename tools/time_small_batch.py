@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Latency of one evaluation at small batch (BASELINE configs 1 and 2, the SA regime) for every
-split / fusion variant of the raster: device time per call from CUDA events around a run of
-back-to-back calls.  Prints one line per (shape, split, fuse) and the automatic choice."""
+split / fusion variant of the raster: device time per call from CUDA events around the replay
+of a CUDA graph that holds 40 back-to-back calls.  Prints one line per (shape, split, fuse) and the automatic choice."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "genetic-gaussian-splats_b200")]
@@ -16,17 +16,30 @@ SHAPES = [("config 1: 128x128, 100 splats, P 32", 128, 100, 32),
           ("512x512, 4000 splats, 1 candidate (final frame)", 512, 4000, 1)]
 
 
-def device_us(fn, n=200):
-    for _ in range(20):
-        fn()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(n):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) * 1e3 / n
+def device_us(fn, n=40, reps=8):
+    """Device time per call: `n` calls captured in ONE CUDA graph and replayed, so the host's
+    per-call overhead (tens of microseconds of Python) does not pace the GPU."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for _ in range(n):
+            fn()
+    graph.replay()
+    best = float("inf")
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e3 / n)
+    return best
 
 
 for name, side, N, B in SHAPES:
