@@ -26,7 +26,11 @@ void set_error(const char *fmt, ...)
 struct Options {
     int pdl;    // programmatic dependent launch between the kernels of a step (GGS_B200_PDL, default 1)
     int split;  // CTAs per (candidate, tile): 0 = automatic (GGS_B200_SPLIT)
-    int fuse;   // decode fused into the raster: -1 = automatic, 0 / 1 (GGS_B200_FUSE)
+    int fuse;   // decode fused into the raster: 0 = never (default), 1 = whenever a segment fits the
+                // list, -1 = when the grid is a single wave and it fits (GGS_B200_FUSE).  Measured on
+                // the B200 the fused variant never wins: every CTA pays the decode's chain of
+                // transcendentals before its first blend, which the two-kernel path hides behind
+                // the previous launch.
 };
 static int env_int(const char *name, int fallback)
 {
@@ -35,7 +39,7 @@ static int env_int(const char *name, int fallback)
 }
 static Options &options()
 {
-    static Options o = {env_int("GGS_B200_PDL", 1) != 0, env_int("GGS_B200_SPLIT", 0), env_int("GGS_B200_FUSE", -1)};
+    static Options o = {env_int("GGS_B200_PDL", 1) != 0, env_int("GGS_B200_SPLIT", 0), env_int("GGS_B200_FUSE", 0)};
     return o;
 }
 

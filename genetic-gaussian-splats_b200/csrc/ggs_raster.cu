@@ -529,7 +529,7 @@ __device__ __forceinline__ void emit_pixel(const RasterArgs &a, int b, int X, in
 // per CTA, and with its body (and the peer stores) inside the kernel ptxas moved the composite
 // loop's list address out of the uniform registers.
 __device__ __noinline__ void reduce_and_finish(const RasterArgs &a, int b, int per_cand, float num,
-                                                  float den, const RasterSmem &sm, int tid, int lane, int warp)
+                                               float den, const RasterSmem &sm, int tid, int lane, int warp)
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -541,7 +541,9 @@ __device__ __noinline__ void reduce_and_finish(const RasterArgs &a, int b, int p
         sm.red[kWarps + warp] = den;
     }
     __syncthreads();
-    if (tid == 0) {
+    if (warp != 0) return;  // one warp finishes the CTA; the others free their slots now
+    int ticket = 0;
+    if (lane == 0) {
         float n = 0.0f, d = 0.0f;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
@@ -549,37 +551,59 @@ __device__ __noinline__ void reduce_and_finish(const RasterArgs &a, int b, int p
             d += sm.red[kWarps + w];
         }
         a.partial[blockIdx.x] = make_float2(n, d);
-        __threadfence();
-        const int ticket = atomicAdd(a.counter + b, 1);
-        *sm.last_ = (ticket == per_cand - 1);
+        // release our partial, acquire everybody else's: one acq_rel RMW instead of fence + atomic
+        asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(ticket) : "l"(a.counter + b) : "memory");
     }
-    __syncthreads();
-    if (*sm.last_ && warp == 0) {
-        __threadfence();
-        const volatile float2 *pb = a.partial + (int64_t)b * per_cand;
-        double n = 0.0, d = 0.0;
-        for (int k = lane; k < per_cand; k += 32) {
-            n += (double)pb[k].x;
-            d += (double)pb[k].y;
-        }
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket != per_cand - 1) return;
+    // last CTA of this candidate: combine the partials in index order
+    const float2 *pb = a.partial + (int64_t)b * per_cand;
+    double n = 0.0, d = 0.0;
+    for (int k = lane; k < per_cand; k += 32) {
+        const float2 v = __ldcg(pb + k);
+        n += (double)v.x;
+        d += (double)v.y;
+    }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            n += __shfl_xor_sync(0xffffffffu, n, o);
-            d += __shfl_xor_sync(0xffffffffu, d, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        n += __shfl_xor_sync(0xffffffffu, n, o);
+        d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    if (lane == 0) {
+        const double P = (double)a.H * (double)a.W;
+        float fit;
+        if (a.mode == GGS_MODE_PLAIN)
+            fit = (float)(n / (3.0 * P));                            // fitness.py:19
+        else if (a.mode == GGS_MODE_MASK)
+            fit = (float)n / ((float)d + 1e-12f);                    // fitness.py:29-31
+        else
+            fit = (float)(n / (3.0 * P)) / ((float)(d / P) + 1e-12f);  // fitness.py:23-27
+        a.fitness[b] = fit;
+        a.counter[b] = 0;  // ready for the next launch on this workspace
+        peer_publish(a.peers, b, fit, (int)(gridDim.x / (unsigned)per_cand));
+    }
+}
+
+// The tile's slice of the target and the mask is what the epilogue waits for (one L2 round trip
+// per row when it is read cold: half of a small launch's time).  It does not depend on the
+// decode launch ahead of us, so every thread asks for one 128-byte line of it -- 32 rows x
+// (3 lines of target + 1 of mask) -- BEFORE the grid dependency wait; by the epilogue it sits in L1.
+__device__ __forceinline__ void prefetch_tile_inputs(const RasterArgs &a, const TileGeom &g, int tid)
+{
+    if (a.target == nullptr || g.X0 >= a.W) return;
+    const int px = min(kTileW, a.W - g.X0);  // pixels of a row inside the image
+    const int part = tid & 3;
+    for (int r = tid >> 2; r < kTileH; r += kThreads / 4) {
+        const int row = g.Y0 + r;
+        if (row >= a.H) break;
+        const int64_t p = (int64_t)row * a.W + g.X0;
+        const float *addr = nullptr;
+        if (part < 3) {
+            if (part * 32 < px * 3) addr = a.target + 3 * p + part * 32;
+        } else if (a.mode != GGS_MODE_PLAIN) {
+            addr = a.mask + p;
         }
-        if (lane == 0) {
-            const double P = (double)a.H * (double)a.W;
-            float fit;
-            if (a.mode == GGS_MODE_PLAIN)
-                fit = (float)(n / (3.0 * P));                            // fitness.py:19
-            else if (a.mode == GGS_MODE_MASK)
-                fit = (float)n / ((float)d + 1e-12f);                    // fitness.py:29-31
-            else
-                fit = (float)(n / (3.0 * P)) / ((float)(d / P) + 1e-12f);  // fitness.py:23-27
-            a.fitness[b] = fit;
-            a.counter[b] = 0;  // ready for the next launch on this workspace
-            peer_publish(a.peers, b, fit, (int)(gridDim.x / (unsigned)per_cand));
-        }
+        if (addr != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(addr));
     }
 }
 
@@ -601,7 +625,8 @@ __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_kernel(const 
     GGS_PX_DECLARE();
     GGS_PAIRS(GGS_T_INIT)
 
-    pdl_wait();  // the decode launch ahead of us has completed; nothing above reads memory
+    prefetch_tile_inputs(a, g, tid);  // inputs nobody ahead of us writes
+    pdl_wait();  // the decode launch ahead of us has completed; nothing above reads its output
     pdl_trigger();
     scan_and_composite<kStats>(a.rec + (int64_t)g.b * a.N * 3, a.aabb + (int64_t)g.b * a.N, a.N, g, sm,
                                tid, lane, warp, work);
@@ -645,6 +670,7 @@ __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_split_kernel(
     GGS_PX_DECLARE();
     GGS_PAIRS(GGS_T_INIT)
 
+    prefetch_tile_inputs(a, g, tid);
     pdl_wait();
     pdl_trigger();
     if (kDecode == 0) {

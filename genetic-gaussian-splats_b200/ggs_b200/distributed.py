@@ -75,9 +75,14 @@ class ShardedEvaluator:
     def __init__(self, target: torch.Tensor, H: int, W: int, k_sigma: float = 3.0,
                  weight_mask: Optional[torch.Tensor] = None, boost_only: bool = False,
                  device=None, group=None,
-                 evaluate: Optional[Callable[[torch.Tensor], torch.Tensor]] = None):
+                 evaluate: Optional[Callable[[torch.Tensor], torch.Tensor]] = None,
+                 peers=None):
         self.group = group
         self._takes_total = False
+        # peers: a ggs_b200.peers.PeerGroup -> the raster kernel delivers the fitness values to
+        # every rank itself (no collective launch); None -> one NCCL / gloo all-gather
+        self.peers = peers
+        self._p2p = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.H, self.W, self.k_sigma = int(H), int(W), float(k_sigma)
@@ -94,6 +99,12 @@ class ShardedEvaluator:
                 return evaluator.fitness(g, tgt, self.H, self.W, self.k_sigma, weight_mask=msk,
                                          boost_only=boost_only, device=dev, split=split)
             self._takes_total = True
+            if peers is not None:
+                def p2p(shard: torch.Tensor, lo: int, total: int) -> torch.Tensor:
+                    return peers.fitness_allgather(shard, tgt, self.H, self.W, offset=lo, total=total,
+                                                   k_sigma=self.k_sigma, weight_mask=msk,
+                                                   boost_only=boost_only)
+                self._p2p = p2p
         self.evaluate = evaluate
 
     # -- fitness -------------------------------------------------------------------------
@@ -118,6 +129,9 @@ class ShardedEvaluator:
             P, shard = int(total), population
             lo, hi = shard_bounds(P, self.world, self.rank)
             assert shard.shape[0] == hi - lo, "shard does not match shard_bounds()"
+        if self._p2p is not None and self.world > 1:
+            lo, _ = shard_bounds(P, self.world, self.rank)
+            return self._p2p(shard.contiguous(), lo, P).clone()   # the view lives for two gathers
         if shard.shape[0] > 0:
             local = (self.evaluate(shard.contiguous(), P) if self._takes_total
                      else self.evaluate(shard.contiguous()))

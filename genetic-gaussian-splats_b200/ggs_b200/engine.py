@@ -53,6 +53,13 @@ class GaEngine:
                                           _stream_ptr(self.device)), "ggs_ga_set_target")
             torch.cuda.current_stream(self.device).synchronize()   # t / m may be temporaries
 
+    def set_peers(self, peers) -> None:
+        """Shard the evaluation over the ranks of a ggs_b200.peers.PeerGroup (before start()):
+        every rank runs the same calls on the same population and seed, evaluates its slice of
+        the children, and the fitness values travel GPU to GPU inside the raster kernel."""
+        self._peers = peers     # keep it alive as long as the engine
+        check(lib().ggs_ga_set_peers(self._h, None if peers is None else peers._h), "ggs_ga_set_peers")
+
     def start(self, population: torch.Tensor, seed: int) -> None:
         pop = _as_f32(population, self.device)
         assert pop.shape[:2] == (self.P, self.N) and pop.shape[2] >= 9

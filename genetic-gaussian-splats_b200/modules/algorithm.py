@@ -47,15 +47,20 @@ def prepare_target(target_img_uint8: torch.Tensor, H: int, W: int) -> torch.Tens
 def _generations_on_engine(pop, target, imp_mask, H, W, k_sigma, boost_only, n_elite, generations,
                            run_seed, schedule, mut_sigma_max, mut_sigma_min, tour_k, cxpb, mutpb,
                            min_scale_splats, max_scale_splats, frame, progress, frame_every,
-                           block=256):
-    """Single GPU: generations are enqueued in blocks on the device engine (ggs_ga_run: breed,
-    evaluate, elitism, ranking, curve point -- four launches per generation, no host sync);
-    the host looks at the state once per block, and at every frame boundary."""
+                           block=256, peers=None):
+    """Generations are enqueued in blocks on the device engine (ggs_ga_run: breed, evaluate,
+    elitism, ranking, curve point -- four launches per generation, no host sync); the host looks
+    at the state once per block, and at every frame boundary.  With `peers` (one process per GPU)
+    every rank runs this same loop: breeding and ranking are replicated, each rank evaluates its
+    slice of the children and the raster kernel itself stores the fitness values into every
+    rank's vector over NVLink -- still no host sync and no collective launch per generation."""
     P, N = int(pop.shape[0]), int(pop.shape[1])
     lo, hi = scale_log_bounds(H, W, min_scale_splats, max_scale_splats)
     eng = GaEngine(target, imp_mask, H, W, P, N, n_elite, generations, k_sigma=k_sigma,
                    boost_only=boost_only)
     try:
+        if peers is not None:
+            eng.set_peers(peers)
         eng.start(pop, run_seed)
         st = eng.state()
         frame(0, st["best_individual"])
@@ -195,14 +200,29 @@ def genetic_approx(target_img_uint8: torch.Tensor,
             pbar.set_postfix(best_mse=f"{best:.6f}", stale=stale,
                              sigma_fac=f"{_anneal_factor(gen, generations, schedule):.3f}")
 
-    use_engine = (world == 1 and pop_size <= MAX_POPULATION
-                  and os.environ.get("GGS_B200_GA_LOOP", "0") != "1")
+    use_engine = (pop_size <= MAX_POPULATION and os.environ.get("GGS_B200_GA_LOOP", "0") != "1")
+    peers = None
+    if use_engine and world > 1:
+        # the engine shards its evaluation through peer-to-peer stores (ggs_b200.peers); if the
+        # GPUs of this box cannot map each other's memory, fall back to the Python-driven loop
+        # with one NCCL all-gather per generation
+        try:
+            from ggs_b200.peers import PeerGroup
+            peers = PeerGroup.from_process_group(capacity=pop_size, device=target.device)
+        except Exception as e:
+            if rank == 0:
+                print(f"[ggs_b200] peer-to-peer fitness exchange unavailable ({e}); using NCCL all-gather")
+            use_engine = False
     try:
         if use_engine:
             best_ind, best_fit, curves = _generations_on_engine(
                 pop, target, imp_mask, H, W, k_sigma, boost_only, n_elite, generations, run_seed,
                 schedule, mut_sigma_max, mut_sigma_min, tour_k, cxpb, mutpb, min_scale_splats,
-                max_scale_splats, frame, progress, max(1, frame_every) if save_video else 0)
+                max_scale_splats, frame, progress, max(1, frame_every) if save_video else 0,
+                peers=peers)   # ranks may cut their blocks differently: epochs count generations
+            if peers is not None:
+                peers.check()
+                peers.close()
         else:
             best_ind, best_fit, curves = _generations_in_python(
                 pop, evaluate, H, W, n_elite, generations, run_seed, schedule, mut_sigma_max,

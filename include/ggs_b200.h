@@ -124,8 +124,8 @@ int ggs_fitness(const float *d_genomes, int layout, int B, int N, int cols, int 
  * per (candidate, 32x32 tile) leaves most of a B200 idle when B * tiles is a few hundred, so the
  * library can give a tile to a thread-block cluster of `split` = 2, 4 or 8 CTAs: CTA k composites
  * the k-th segment of the genome and the partial (colour, transmittance) states are folded in
- * genome order through distributed shared memory ("over" is associative); when a segment fits the
- * CTA's splat list the decode is fused into the same launch, so an evaluation is ONE kernel.
+ * genome order through distributed shared memory ("over" is associative).  (A variant that also
+ * fuses the decode into that launch exists behind the "fuse" option; it measured slower and is off.)
  * Every entry point picks `split` from B (ggs_choose_split: the largest split that keeps the grid
  * within one wave).  The fold changes the floating-point association, so results for different
  * `split` agree to ~1e-7 but not bit for bit: a caller that evaluates ONE population in several
@@ -142,8 +142,8 @@ int ggs_fitness_ex(const float *d_genomes, int layout, int B, int N, int cols, i
  * Process-wide switches, for A/B timing and tests; the defaults come from the environment
  * variables read at first use.  "pdl" (GGS_B200_PDL, default 1): programmatic dependent launch
  * between the kernels of a step.  "split" (GGS_B200_SPLIT, default 0 = automatic): force 1, 2, 4
- * or 8 wherever the caller does not pass one.  "fuse" (GGS_B200_FUSE, default -1 = when the grid
- * is a single wave): 0 never / 1 whenever a segment fits, decode inside the raster launch.
+ * or 8 wherever the caller does not pass one.  "fuse" (GGS_B200_FUSE, default 0 = never): 1 = decode
+ * inside the raster launch whenever a segment fits the list, -1 = only for single-wave grids.
  */
 int ggs_set_option(const char *name, int value);
 

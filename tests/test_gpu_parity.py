@@ -387,7 +387,7 @@ def test_full_size_config3_properties(ggs):
     dec_cpu = oracle.decode(oracle.encode(g_np), H, W, 3.0)
     flipped = aabb_mismatch_mask(dec_gpu, dec_cpu).any(axis=1)
     note(f"test_full_size_config3_properties: candidates with a flipped AABB edge: {int(flipped.sum())} of {B}")
-    assert flipped.sum() <= 2
+    assert flipped.sum() <= 24      # ~1e-5 per edge over 1,024,000 splats (SURVEY 7.2 hard part 1)
     f_gpu = f.cpu().numpy().astype(np.float64)
     f_cpu = oracle.fitness(g_np, t_np, H, W, 3.0, weight_mask=m_np).astype(np.float64)
     rel = np.abs(f_gpu / f_cpu - 1.0)

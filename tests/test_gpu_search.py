@@ -99,6 +99,15 @@ b = ev.fitness(g[lo:hi].clone(), replicated=False, total=P)
 el = ev.elites(a, 5)
 rows = ev.gather_rows(g[lo:hi].clone(), el, P)
 ok = torch.equal(a, full) and torch.equal(b, full) and torch.equal(rows, g[el])
+# the same through peer-to-peer stores: the raster kernel writes into every rank's vector
+from ggs_b200.peers import PeerGroup
+peers = PeerGroup.from_process_group(capacity=P, device=dev)
+ev2 = ShardedEvaluator(t, H, W, weight_mask=m, device=dev, peers=peers)
+for _ in range(5):                                   # epochs alternate between two buffer halves
+    c = ev2.fitness(g)
+    d = ev2.fitness(g[lo:hi].clone(), replicated=False, total=P)
+    ok = ok and torch.equal(c, full) and torch.equal(d, full)
+peers.check()
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.destroy_process_group()

@@ -23,7 +23,7 @@ def ggs():
     import ggs_b200
     ggs_b200.lib()
     yield ggs_b200
-    ggs_b200.set_option("fuse", -1)
+    ggs_b200.set_option("fuse", 0)
     ggs_b200.set_option("split", 0)
 
 
@@ -65,9 +65,15 @@ def test_split_and_fused_against_oracle(ggs, B, N, H, W, seed, late, split):
             kw_gpu = {k2: (cuda(v) if isinstance(v, np.ndarray) else v) for k2, v in kw.items()}
             f = ggs.fitness(cuda(g), cuda(t), H, W, 3.0, split=split, **kw_gpu).cpu().numpy()
             np.testing.assert_allclose(f, f_cpu, rtol=FIT_RTOL)
-    ggs.set_option("fuse", -1)
-    # fused decode = decode kernel + raster, bit for bit (same arithmetic, same order)
-    assert np.array_equal(got[0][0], got[1][0]) and np.array_equal(got[0][1], got[1][1])
+    ggs.set_option("fuse", 0)
+    # fused decode = decode kernel + raster: the same records, hence the same image bit for bit;
+    # the same fitness bits too, except at split 1, where the two-kernel path is the throughput
+    # kernel and sums a tile's squared errors in another order
+    assert np.array_equal(got[0][1], got[1][1])
+    if split > 1:
+        assert np.array_equal(got[0][0], got[1][0])
+    else:
+        np.testing.assert_allclose(got[0][0], got[1][0], rtol=1e-6)
 
 
 def test_a_given_split_is_deterministic_and_independent_of_the_call_boundaries(ggs):
@@ -83,7 +89,7 @@ def test_a_given_split_is_deterministic_and_independent_of_the_call_boundaries(g
             parts = torch.cat([ggs.fitness(g[:3], t, H, W, 3.0, split=split),
                                ggs.fitness(g[3:], t, H, W, 3.0, split=split)])
             assert torch.equal(f1, parts), (split, fuse)
-    ggs.set_option("fuse", -1)
+    ggs.set_option("fuse", 0)
     # different splits agree to rounding, not bit for bit (the fold re-associates the blend)
     a, b = ggs.fitness(g, t, H, W, 3.0, split=1), ggs.fitness(g, t, H, W, 3.0, split=8)
     np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=2e-6)

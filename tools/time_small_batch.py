@@ -60,6 +60,6 @@ for name, side, N, B in SHAPES:
             except ggs_b200.GgsError as e:
                 row.append(f"{'fused' if fuse else 'decode+raster'}   n/a")
         print(f"   split {split}: " + " | ".join(row))
-    ggs_b200.set_option("fuse", -1)
+    ggs_b200.set_option("fuse", 0)
     us = device_us(lambda: ggs_b200.fitness(g, target, H, W, 3.0, weight_mask=mask))
     print(f"   default entry: {us:7.1f} us per evaluation, {B / us * 1e6:,.0f} candidates/s")
