@@ -594,6 +594,7 @@ struct ggs_sa {
     uint64_t seed = 0;
     int iteration = -1;
     bool has_target = false;
+    bool sequential = true;  // the reference's chain (annealing.py:121-146); false: batched neighbours
 };
 
 extern "C" {
@@ -756,13 +757,6 @@ int ggs_sa_run(ggs_sa *g, int count, const float *h_sigma6, const double *h_temp
     GGS_TRY(cudaSetDevice(g->device));
     for (int k = 0; k < count; ++k) {
         const int it = g->iteration + 1;
-        // `tries` independently mutated copies of the current state: the breeding kernel with a
-        // one-individual population and no crossover (annealing.py:121-128, batched)
-        GGS_TRY(launch_breed(g->current, g->dummy_fit, 1, g->N, 9, g->tries, g->cand, 1, 0.0f, mutpb,
-                             h_sigma6 + 6 * (size_t)k, log_scale_lo, log_scale_hi, g->seed,
-                             (uint32_t)it, st));
-        int rc = sa_energy(g, g->cand, g->tries, st);
-        if (rc) return rc;
         MetropolisParams q = {};
         q.cand = g->cand;
         q.energy = g->energy;
@@ -772,12 +766,47 @@ int ggs_sa_run(ggs_sa *g, int count, const float *h_sigma6, const double *h_temp
         q.e_best = g->e_best;
         q.curve = g->curves + (size_t)it * 2;
         q.temperature = h_temperature[k];
-        for (int t = 0; t < g->tries; ++t) q.uniform[t] = h_uniform[(size_t)k * g->tries + t];
-        q.tries = g->tries;
         q.N = g->N;
-        GGS_TRY(launch_kernel(metropolis_kernel, 1, kSelectThreads, 0, st, q));
+        if (g->sequential) {
+            // The reference's chain (annealing.py:121-146): every try mutates the state the previous
+            // try left behind, is evaluated on its own (B = 1: the raster's 8-way split) and is
+            // accepted or rejected before the next one is proposed.  Proposal number
+            // (it - 1) * tries + t + 1 keys the random stream, as in the Python-driven loop.
+            for (int t = 0; t < g->tries; ++t) {
+                GGS_TRY(launch_breed(g->current, g->dummy_fit, 1, g->N, 9, 1, g->cand, 1, 0.0f, mutpb,
+                                     h_sigma6 + 6 * (size_t)k, log_scale_lo, log_scale_hi, g->seed,
+                                     (uint32_t)((size_t)(it - 1) * g->tries + t + 1), st));
+                int rc = sa_energy(g, g->cand, 1, st);
+                if (rc) return rc;
+                q.uniform[0] = h_uniform[(size_t)k * g->tries + t];
+                q.tries = 1;
+                GGS_TRY(launch_kernel(metropolis_kernel, 1, kSelectThreads, 0, st, q));
+            }
+        } else {
+            // `tries` independently mutated copies of the current state: the breeding kernel with a
+            // one-individual population and no crossover (annealing.py:121-128, batched), one
+            // evaluation of all of them, the Metropolis tests applied in order
+            GGS_TRY(launch_breed(g->current, g->dummy_fit, 1, g->N, 9, g->tries, g->cand, 1, 0.0f, mutpb,
+                                 h_sigma6 + 6 * (size_t)k, log_scale_lo, log_scale_hi, g->seed,
+                                 (uint32_t)it, st));
+            int rc = sa_energy(g, g->cand, g->tries, st);
+            if (rc) return rc;
+            for (int t = 0; t < g->tries; ++t) q.uniform[t] = h_uniform[(size_t)k * g->tries + t];
+            q.tries = g->tries;
+            GGS_TRY(launch_kernel(metropolis_kernel, 1, kSelectThreads, 0, st, q));
+        }
         g->iteration = it;
     }
+    return GGS_OK;
+}
+
+int ggs_sa_set_mode(ggs_sa *g, int batched_neighbours)
+{
+    if (!g) {
+        set_error("ggs_sa_set_mode: NULL engine");
+        return GGS_EINVAL;
+    }
+    g->sequential = (batched_neighbours == 0);
     return GGS_OK;
 }
 

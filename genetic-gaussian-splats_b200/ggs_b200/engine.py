@@ -135,13 +135,18 @@ class SaEngine:
 
     def __init__(self, target: torch.Tensor, weight_mask: Optional[torch.Tensor], H: int, W: int,
                  N: int, tries: int, max_iterations: int, *, k_sigma: float = 3.0,
-                 boost_only: bool = False, boost_beta: float = 1.0, device=None):
+                 boost_only: bool = False, boost_beta: float = 1.0, device=None,
+                 batch_neighbors: bool = False):
+        """batch_neighbors=False: the reference's chain, every try starts from the state the
+        previous one left (annealing.py:121-146); True: all tries of an iteration are proposed
+        from the same state and scored by one evaluation (BASELINE config 2)."""
         self.device = _cuda_device(device if device is not None else target.device)
         self.N, self.H, self.W, self.tries = int(N), int(H), int(W), int(tries)
         self._h = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             check(lib().ggs_sa_create(self.device.index or 0, self.N, self.H, self.W, self.tries,
                                       int(max_iterations), ctypes.byref(self._h)), "ggs_sa_create")
+            check(lib().ggs_sa_set_mode(self._h, 1 if batch_neighbors else 0), "ggs_sa_set_mode")
             t = _as_f32(target, self.device)
             assert t.shape == (self.H, self.W, 3), "target must be [H, W, 3]"
             m = None if weight_mask is None else _as_f32(weight_mask, self.device)

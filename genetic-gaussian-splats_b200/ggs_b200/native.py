@@ -56,6 +56,7 @@ SIGNATURES = {
     "ggs_ga_population": (_i, [_vp, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     "ggs_sa_create": (_i, [_i, _i, _i, _i, _i, _i, ctypes.POINTER(_vp)]),
     "ggs_sa_destroy": (None, [_vp]),
+    "ggs_sa_set_mode": (_i, [_vp, _i]),
     "ggs_sa_set_target": (_i, [_vp, _vp, _vp, _i, _f, _f, _vp]),
     "ggs_sa_start": (_i, [_vp, _vp, _i, ctypes.c_uint64, _vp]),
     "ggs_sa_run": (_i, [_vp, _i, ctypes.POINTER(_f), ctypes.POINTER(_d), ctypes.POINTER(_d), _f, _f,

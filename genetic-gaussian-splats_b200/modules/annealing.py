@@ -1,13 +1,19 @@
 """Simulated annealing (reference: modules/annealing.py:29-190), same entry point.
 
-The reference runs `tries_per_iter` strictly sequential tries per iteration, each a B=1
-evaluation.  Here all tries of an iteration are proposed from the current state and evaluated
-in ONE launch (B = tries_per_iter, BASELINE config 2 "batched neighbour proposals"), then the
-Metropolis test is applied to them in order.  This changes the chain slightly -- a later try no
-longer starts from an earlier accepted try of the same iteration -- and is switched off with
-batch_neighbors=False, which reproduces the reference's sequential scheme.  On one GPU the
-batched iterations run on the device engine (ggs_sa_run) without the host in the loop;
-GGS_B200_SA_LOOP=1 drives the same chain from Python instead (same result bit for bit)."""
+Two schemes, both on the device engine (ggs_sa_run: no host in the loop; GGS_B200_SA_LOOP=1
+drives the same chain from Python instead, same result bit for bit):
+
+* batch_neighbors=False (DEFAULT) -- the reference's chain: `tries_per_iter` strictly sequential
+  tries per iteration, each mutating the state the previous try left behind and evaluated on its
+  own (B = 1, annealing.py:121-146).  Iterations are 1:1 with the reference's.
+* batch_neighbors=True -- BASELINE config 2 "batched neighbour proposals": all tries of an
+  iteration are proposed from the SAME state and scored by ONE evaluation, then the Metropolis
+  test is applied to them in order.  About 4x the iterations per second, but NOT the reference's
+  chain: a later try no longer starts from an earlier accepted try, so an iteration makes at most
+  one effective move where the reference can make up to `tries_per_iter`; curves are not
+  comparable iteration by iteration.
+
+The scheme in use is printed once at the start of a run."""
 from __future__ import annotations
 
 import math
@@ -52,14 +58,15 @@ def _temp_schedule(kind: str, T0: float, i: int, total: int) -> float:
 
 def _iterations_on_engine(curr, target, imp_mask, H, W, k_sigma, boost_only, iterations, run_seed,
                           temp0, temp_schedule, sigma_schedule, mut_sigma_max, mut_sigma_min, mutpb,
-                          min_scale_splats, max_scale_splats, tries, frame, frame_every, block=256):
+                          min_scale_splats, max_scale_splats, tries, batch_neighbors, frame,
+                          frame_every, block=256):
     """Iterations enqueued in blocks on the device engine (ggs_sa_run: propose, evaluate,
-    Metropolis -- four launches per iteration, no host sync); the host looks at the state once
-    per block, and at every frame boundary.  Same chain as _iterations_in_python with
-    batch_neighbors=True, bit for bit."""
+    Metropolis -- four launches per try, or per iteration when the neighbours are batched; no
+    host sync); the host looks at the state once per block, and at every frame boundary.  Same
+    chain as _iterations_in_python with the same batch_neighbors, bit for bit."""
     lo, hi = scale_log_bounds(H, W, min_scale_splats, max_scale_splats)
     eng = SaEngine(target, imp_mask, H, W, int(curr.shape[0]), tries, iterations, k_sigma=k_sigma,
-                   boost_only=boost_only)
+                   boost_only=boost_only, batch_neighbors=batch_neighbors)
     try:
         eng.start(curr, run_seed)
         frame(0, eng.state()["best_state"])
@@ -111,10 +118,10 @@ def _iterations_in_python(curr, energy, propose, iterations, temp0, temp_schedul
         for it in pbar:
             T = _temp_schedule(temp_schedule, temp0, it, iterations)
             accepted_any = False
+            uniforms = [random.random() for _ in range(tries)]  # one per try, used if uphill
             if batch_neighbors:
                 neighbours = propose(curr, tries, it)
                 energies = energy(neighbours)
-                uniforms = [random.random() for _ in range(tries)]  # one per try, used if uphill
             for k in range(tries):
                 if batch_neighbors:
                     cand, e_new = neighbours[k], float(energies[k])
@@ -122,8 +129,7 @@ def _iterations_in_python(curr, energy, propose, iterations, temp0, temp_schedul
                     cand = propose(curr, 1, it)[0]
                     e_new = float(energy(cand.unsqueeze(0))[0])
                 dE = e_new - e_curr
-                if dE <= 0.0 or (T > 0.0 and (uniforms[k] if batch_neighbors else random.random())
-                                 < math.exp(-dE / T)):
+                if dE <= 0.0 or (T > 0.0 and uniforms[k] < math.exp(-dE / T)):
                     curr, e_curr, accepted_any = cand.clone(), e_new, True
                 if e_curr + 1e-12 < best_fit:
                     best_fit, best = e_curr, curr.clone()
@@ -168,9 +174,11 @@ def simulated_annealing(
     loss_png_path: str = "",
     loss_csv_path: str = "",
     loss_log_y: bool = False,
-    batch_neighbors: bool = True,
+    batch_neighbors: bool = False,
 ) -> Tuple[torch.Tensor, float]:
-    """Minimises the (masked) MSE energy; returns (best axes-angle individual on CPU, best MSE)."""
+    """Minimises the (masked) MSE energy; returns (best axes-angle individual on CPU, best MSE).
+    batch_neighbors=False is the reference's sequential chain; True evaluates the tries of an
+    iteration in one launch (a different chain, see the module docstring)."""
     target = prepare_target(target_img_uint8, H, W).to(device)
     imp_mask = compute_importance_mask(target, H, W, edge_scales=(1, 2, 4), w_edge=0.7, w_var=0.3,
                                        gamma=0.7, floor=0.15, smooth=3, strength=mask_strength)
@@ -205,12 +213,18 @@ def simulated_annealing(
             save_frame_png(it, state.to(device), pad, prefix, video_dir, H, W, k_sigma, device,
                            save_video)
 
-    if (batch_neighbors and curr.is_cuda and tries <= MAX_TRIES
-            and os.environ.get("GGS_B200_SA_LOOP", "0") != "1"):
+    print(f"[ggs_b200] simulated annealing, {tries} tries per iteration: " +
+          ("batched neighbours -- all tries of an iteration start from the same state and are scored "
+           "by one launch (NOT the reference's chain: at most one effective move per iteration)"
+           if batch_neighbors and tries > 1 else
+           "sequential tries, each from the state the previous one left (the reference's chain)"),
+          flush=True)
+    if curr.is_cuda and tries <= MAX_TRIES and os.environ.get("GGS_B200_SA_LOOP", "0") != "1":
         best, best_fit, curves = _iterations_on_engine(
             curr, target, imp_mask, H, W, k_sigma, boost_only, iterations, run_seed, temp0,
             temp_schedule, sigma_schedule, mut_sigma_max, mut_sigma_min, mutpb, min_scale_splats,
-            max_scale_splats, tries, frame, max(1, frame_every) if save_video else 0)
+            max_scale_splats, tries, batch_neighbors, frame,
+            max(1, frame_every) if save_video else 0)
     else:
         best, best_fit, curves = _iterations_in_python(
             curr, energy, propose, iterations, temp0, temp_schedule, sigma_schedule, tries,

@@ -232,18 +232,27 @@ int ggs_ga_population(ggs_ga *ga, const float **d_population, const float **d_fi
 /* ---- simulated annealing on the device ---------------------- */
 
 /*
- * The iteration loop of modules/annealing.py:112-150 with batched neighbour proposals
- * (BASELINE config 2): per iteration `tries` independently mutated copies of the current state
- * (the breeding kernel with a one-individual population and no crossover, annealing.py:121-128),
- * ONE evaluation of all of them, and the Metropolis test applied to them in order
- * (annealing.py:129-137: accept when dE <= 0 or u < exp(-dE / T); the best-so-far test follows
- * every try).  ggs_sa_run only ENQUEUES work (four launches per iteration on `stream`); the
- * temperature schedule, the annealed sigmas and the U[0,1) draws stay with the caller and are
- * passed per iteration.  The engine owns its device memory.  Limits: tries <= 64.
+ * The iteration loop of modules/annealing.py:112-150 on the device, in two schemes
+ * (ggs_sa_set_mode):
+ *   sequential (default, the reference's chain, annealing.py:121-146): each of the `tries` of an
+ *     iteration mutates the state the previous try left behind (the breeding kernel with a
+ *     one-individual population and no crossover), is evaluated on its own (B = 1, the raster's
+ *     split path) and passes the Metropolis test -- accept when dE <= 0 or u < exp(-dE / T), the
+ *     best-so-far test follows every try -- before the next one is proposed: 4 launches per try;
+ *   batched (BASELINE config 2, "batched neighbour proposals"): `tries` independently mutated
+ *     copies of the current state, ONE evaluation of all of them, the Metropolis tests applied to
+ *     them in order: 4 launches per iteration, but a later try no longer starts from an accepted
+ *     earlier try of the same iteration, so iterations are not 1:1 with the reference's.
+ * ggs_sa_run only ENQUEUES work on `stream`; the temperature schedule, the annealed sigmas and
+ * the U[0,1) draws stay with the caller and are passed per iteration.  The engine owns its
+ * device memory.  Limits: tries <= 64.
  */
 typedef struct ggs_sa ggs_sa;
 int ggs_sa_create(int device, int N, int H, int W, int tries, int max_iterations, ggs_sa **out);
 void ggs_sa_destroy(ggs_sa *sa);
+/* batched_neighbours = 0: the reference's sequential tries (default); != 0: one evaluation of all
+ * tries per iteration.  May be changed between ggs_sa_run calls. */
+int ggs_sa_set_mode(ggs_sa *sa, int batched_neighbours);
 /* As ggs_ga_set_target. */
 int ggs_sa_set_target(ggs_sa *sa, const float *d_target, const float *d_mask, int mode,
                       float boost_beta, float k_sigma, void *stream);

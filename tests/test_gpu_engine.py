@@ -167,14 +167,23 @@ def test_genetic_approx_engine_equals_python_loop(ggs, tmp_path):
 
 # ---- simulated annealing engine (ggs_sa_*) -----------------------------------------------------
 
-def host_sa_iteration(ggs, cur, e_cur, best, e_best, t, m, H, W, tries, it, seed, T, uniforms):
-    """One batched iteration with the public device ops; Metropolis on the host
-    (annealing.py:125-137)."""
-    nb = cur.unsqueeze(0).repeat(tries, 1, 1).contiguous()
-    cand = ggs.breed(nb, torch.zeros(tries, device="cuda"), SIG, tour_k=1, cxpb=0.0, mutpb=0.1,
-                     log_scale_lo=LO, log_scale_hi=HI, seed=seed, generation=it)
-    en = ggs.fitness(cand, t, H, W, 3.0, weight_mask=m).cpu().tolist()
+def host_sa_iteration(ggs, cur, e_cur, best, e_best, t, m, H, W, tries, it, seed, T, uniforms,
+                      batched=True):
+    """One iteration with the public device ops; Metropolis on the host (annealing.py:121-146):
+    batched (all neighbours from the same state, one evaluation) or the reference's sequential
+    tries (each from the state the previous one left, proposal number keys the random stream)."""
+    if batched:
+        nb = cur.unsqueeze(0).repeat(tries, 1, 1).contiguous()
+        cand = ggs.breed(nb, torch.zeros(tries, device="cuda"), SIG, tour_k=1, cxpb=0.0, mutpb=0.1,
+                         log_scale_lo=LO, log_scale_hi=HI, seed=seed, generation=it)
+        en = ggs.fitness(cand, t, H, W, 3.0, weight_mask=m).cpu().tolist()
     for k in range(tries):
+        if not batched:
+            one = ggs.breed(cur.unsqueeze(0).contiguous(), torch.zeros(1, device="cuda"), SIG, tour_k=1,
+                            cxpb=0.0, mutpb=0.1, log_scale_lo=LO, log_scale_hi=HI, seed=seed,
+                            generation=(it - 1) * tries + k + 1)
+            cand = {k: one[0]}
+            en = {k: float(ggs.fitness(one, t, H, W, 3.0, weight_mask=m)[0])}
         dE = en[k] - e_cur
         if dE <= 0.0 or (T > 0.0 and uniforms[k] < math.exp(-dE / T)):
             cur, e_cur = cand[k].clone(), en[k]
@@ -183,13 +192,14 @@ def host_sa_iteration(ggs, cur, e_cur, best, e_best, t, m, H, W, tries, it, seed
     return cur, e_cur, best, e_best
 
 
+@pytest.mark.parametrize("batched", [True, False])
 @pytest.mark.parametrize("N,tries,T0", [(40, 8, 2e-3), (33, 1, 1e-3), (12, 64, 5e-3), (25, 5, 0.0)])
-def test_sa_engine_iterations_match_host_metropolis(ggs, N, tries, T0):
+def test_sa_engine_iterations_match_host_metropolis(ggs, N, tries, T0, batched):
     from ggs_b200.engine import SaEngine
-    H, W, I, seed = 48, 64, 14, 31
+    H, W, I, seed = 48, 64, 14 if batched or tries < 64 else 4, 31
     pop, t, m = setup(1, N, H, W, seed=N)
     rng = np.random.default_rng(tries)
-    eng = SaEngine(t, m, H, W, N, tries, I)
+    eng = SaEngine(t, m, H, W, N, tries, I, batch_neighbors=batched)
     eng.start(pop[0], seed)
     cur = pop[0].clone()
     e_cur = float(ggs.fitness(pop, t, H, W, 3.0, weight_mask=m)[0])
@@ -204,7 +214,7 @@ def test_sa_engine_iterations_match_host_metropolis(ggs, N, tries, T0):
         eng.run([SIG], [T], [u], 0.1, LO, HI)
         before = e_cur
         cur, e_cur, best, e_best = host_sa_iteration(ggs, cur, e_cur, best, e_best, t, m, H, W, tries,
-                                                     it, seed, T, u)
+                                                     it, seed, T, u, batched=batched)
         uphill_accepts += e_cur > before
         st = eng.state(curves_from=it)
         assert st["iteration"] == it
@@ -214,6 +224,8 @@ def test_sa_engine_iterations_match_host_metropolis(ggs, N, tries, T0):
         assert st["curves"].tolist() == [[e_best, e_cur]]
     if T0 == 0.0:
         assert uphill_accepts == 0
+    elif tries == 8:
+        assert uphill_accepts > 0          # the Metropolis branch is exercised
     assert eng.state()["curves"].shape == (I + 1, 2)
     eng.close()
 
@@ -226,8 +238,8 @@ def test_sa_engine_blocks_equal_single_steps(ggs):
     temps = [3e-3 * (1.0 - g / I) for g in range(I)]
     uni = np.random.default_rng(0).random((I, tries)).tolist()
     out = []
-    for block in (I, 1, 5):
-        eng = SaEngine(t, None if block == 5 else m, H, W, N, tries, I)
+    for block, batched in ((I, True), (1, True), (5, True), (I, False), (4, False)):
+        eng = SaEngine(t, None if block == 5 else m, H, W, N, tries, I, batch_neighbors=batched)
         eng.start(pop[0], 9)
         for g0 in range(0, I, block):
             eng.run(rows[g0:g0 + block], temps[g0:g0 + block], uni[g0:g0 + block], 0.1, LO, HI)
@@ -237,6 +249,10 @@ def test_sa_engine_blocks_equal_single_steps(ggs):
     assert out[1][0] == out[0][0] and torch.equal(out[1][1], out[0][1])
     assert np.array_equal(out[1][2], out[0][2]) and torch.equal(out[1][3], out[0][3])
     assert out[2][0] != out[0][0]          # the plain (unmasked) energy is a different run
+    # sequential tries: blocks equal blocks, and the chain differs from the batched one
+    assert out[4][0] == out[3][0] and torch.equal(out[4][1], out[3][1])
+    assert np.array_equal(out[4][2], out[3][2]) and torch.equal(out[4][3], out[3][3])
+    assert not np.array_equal(out[3][2], out[0][2])
 
 
 def test_sa_engine_errors(ggs):
@@ -267,6 +283,14 @@ def test_simulated_annealing_engine_equals_python_loop(ggs, tmp_path):
               mut_sigma_min=C.MUT_SIGMA_MIN, sigma_schedule="cosine", min_scale_splats=3.0,
               max_scale_splats=0.1, k_sigma=3.0, mask_strength=0.7, boost_only=False, iterations=45,
               temp0=2e-3, temp_schedule="cosine", tries_per_iter=8)
+    for batched in (False, True):
+        _sa_engine_vs_loop(target, dict(kw, batch_neighbors=batched), tmp_path / f"b{int(batched)}")
+
+
+def _sa_engine_vs_loop(target, kw, tmp_path):
+    from modules.annealing import simulated_annealing
+    import random
+    tmp_path.mkdir()
     runs = []
     for loop, frames in (("0", False), ("1", False), ("0", True)):
         os.environ["GGS_B200_SA_LOOP"] = loop

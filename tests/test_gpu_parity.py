@@ -312,7 +312,8 @@ def test_modules_entry_points(ggs, golden):
     assert np.abs(img.cpu().numpy()[:n] - golden["images"]).max() <= IMG_TOL
     one = render_splats_rgb_triton(genome_to_renderer(axes[0]), H, W, k_sigma=k, device="cuda")
     assert one.shape == (1, H, W, 3)  # 2-D input keeps B = 1 (render.py:220-221)
-    assert torch.equal(one[0], img[0])
+    # a single frame may take the small-batch path (other split than the batch): equal to rounding
+    assert (one[0] - img[0]).abs().max().item() <= 2e-6
 
     fm = fitness_many(pop, t, H, W, k, "cuda", tile=32, weight_mask=m)
     np.testing.assert_allclose(fm.cpu().numpy(), golden["fit_mask"], rtol=FIT_RTOL)

@@ -41,13 +41,13 @@ def ga(side, N, P, steps):
     print(f"GA  {side}x{side}, {N} splats, population {P}: {min(out['1']):9.1f} us/generation with PDL, "
           f"{min(out['0']):9.1f} without ({1e6 / min(out['1']):.0f} generations/s)")
 
-def sa(side, N, tries, steps):
+def sa(side, N, tries, steps, batched=True):
     H = W = side
     t = synth.synthetic_target_np(H, W, 3)
     tgt, m = torch.from_numpy(t).cuda(), torch.from_numpy(synth.importance_mask_np(t)).cuda()
     state = torch.from_numpy(synth.new_population_np(1, N, H, W, seed=1)).cuda()[0]
     lo, hi = scale_log_bounds(H, W, C.MIN_SCALE_SPLATS, C.MAX_SCALE_SPLATS)
-    eng = SaEngine(tgt, m, H, W, N, tries, 8 * steps + 8)
+    eng = SaEngine(tgt, m, H, W, N, tries, 8 * steps + 8, batch_neighbors=batched)
     eng.start(state, 7)
     rows = [build_mut_sigma(1, 100, C.SCHEDULE, C.MUT_SIGMA_MAX, C.MUT_SIGMA_MIN)] * steps
     uni = np.random.default_rng(0).random((steps, tries))
@@ -58,7 +58,8 @@ def sa(side, N, tries, steps):
         ggs_b200.set_option("pdl", int(pdl))
         out.setdefault(pdl, []).append(events(block, 2))
     eng.close()
-    print(f"SA  {side}x{side}, {N} splats, {tries} tries: {min(out['1']):9.1f} us/iteration with PDL, "
+    print(f"SA  {side}x{side}, {N} splats, {tries} tries ({'batched' if batched else 'sequential, the reference chain'}): "
+          f"{min(out['1']):9.1f} us/iteration with PDL, "
           f"{min(out['0']):9.1f} without ({1e6 / min(out['1']):.0f} iterations/s)")
 
 ga(128, 100, 32, 400)
@@ -68,3 +69,5 @@ ga(512, 4000, 1024, 6)
 sa(256, 500, 8, 400)
 sa(256, 500, 1, 400)
 sa(256, 500, 64, 200)
+sa(256, 500, 8, 200, batched=False)
+sa(256, 512, 8, 200, batched=False)

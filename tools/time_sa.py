@@ -19,15 +19,18 @@ kw = dict(H=H, W=W, device="cuda", n_splats=N, mutpb=C.MUTPB, mut_sigma_max=C.MU
           max_scale_splats=0.1, k_sigma=3.0, mask_strength=0.7, boost_only=False, temp0=1e-4,
           temp_schedule="exp", tries_per_iter=TRIES)
 simulated_annealing(target, iterations=50, **kw)   # warm-up (context, mask workspace)
-for loop in ("0", "1"):
-    os.environ["GGS_B200_SA_LOOP"] = loop
-    res = []
-    for iters in (0, ITERS):
-        torch.manual_seed(1); random.seed(1)
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        _, e = simulated_annealing(target, iterations=iters, **kw)
-        torch.cuda.synchronize(); res.append((time.perf_counter() - t0, e))
-    dt = res[1][0] - res[0][0]
-    print(f"{'python loop' if loop == '1' else 'device engine'}: {H}x{W}, {N} splats, {TRIES} tries/iteration: "
-          f"{ITERS} iterations in {dt:.3f} s beyond the {res[0][0]:.3f} s set-up = {ITERS / dt:.0f} iterations/s "
-          f"({ITERS * TRIES / dt:.0f} tries/s); energy {res[0][1]:.6f} -> {res[1][1]:.6f}")
+for batched in (False, True):
+  kw["batch_neighbors"] = batched
+  print("batched neighbours" if batched else "sequential tries (the reference's chain)")
+  for loop in ("0", "1"):
+      os.environ["GGS_B200_SA_LOOP"] = loop
+      res = []
+      for iters in (0, ITERS):
+          torch.manual_seed(1); random.seed(1)
+          torch.cuda.synchronize(); t0 = time.perf_counter()
+          _, e = simulated_annealing(target, iterations=iters, **kw)
+          torch.cuda.synchronize(); res.append((time.perf_counter() - t0, e))
+      dt = res[1][0] - res[0][0]
+      print(f"{'python loop' if loop == '1' else 'device engine'}: {H}x{W}, {N} splats, {TRIES} tries/iteration: "
+            f"{ITERS} iterations in {dt:.3f} s beyond the {res[0][0]:.3f} s set-up = {ITERS / dt:.0f} iterations/s "
+            f"({ITERS * TRIES / dt:.0f} tries/s); energy {res[0][1]:.6f} -> {res[1][1]:.6f}")
