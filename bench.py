@@ -349,6 +349,98 @@ def run_reference(args, wl):
 
 # ------------------------------------------------------------------------------ our arm
 
+def config4_leg(rank, world, dev, peers, steps=3):
+    """BASELINE config 4: GA at 512x512, 4,000 splats, population 8,192 sharded over the N GPUs.
+    (a) the evaluation of the whole population (each rank its 8,192 / N slice, fitness gathered
+    on every rank); (b) a WHOLE generation on the device engine -- breed, evaluate the children,
+    gather, elitism + ranking -- with no host sync.  Max over ranks, CUDA events."""
+    import torch
+    import torch.distributed as dist
+    import ggs_b200
+    from ggs_b200 import synth
+    from ggs_b200.distributed import shard_bounds
+    from ggs_b200.engine import GaEngine
+    from modules.population import new_population
+    from modules.utils import build_mut_sigma, scale_log_bounds
+    import modules.config as C
+    H = W = 512
+    N, P, n_elite = 4000, 8192, 8
+    t_np = synth.synthetic_target_np(H, W, 0)
+    target = torch.from_numpy(t_np).to(dev)
+    mask = ggs_b200.importance_mask(target, H, W, edge_scales=(1, 2, 4), w_edge=0.7, w_var=0.3,
+                                    gamma=0.7, floor=0.15, smooth=3, strength=0.7)
+    torch.manual_seed(42)                       # the same population on every rank
+    pop = new_population(P, N, H, W, 3.0, 0.1, device=dev)
+    lo, hi = shard_bounds(P, world, rank)
+
+    def timed(fn, n):
+        fn()
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) / n], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # the yardstick: 1,024 candidates of this shape on ONE GPU, no exchange
+    base_ms = timed(lambda: ggs_b200.fitness(pop[lo:lo + 1024], target, H, W, 3.0, weight_mask=mask), steps)
+    base_rate = 1024 / (base_ms * 1e-3)
+
+    if world > 1 and peers is not None:
+        def evaluate():
+            return peers.fitness_allgather(pop[lo:hi], target, H, W, offset=lo, total=P, weight_mask=mask)
+    elif world > 1:
+        full = torch.empty((P,), dtype=torch.float32, device=dev)
+        split = ggs_b200.choose_split(P, N, H, W)
+
+        def evaluate():
+            dist.all_gather_into_tensor(full, ggs_b200.fitness(pop[lo:hi], target, H, W, 3.0,
+                                                               weight_mask=mask, split=split))
+            return full
+    else:
+        def evaluate():
+            return ggs_b200.fitness(pop, target, H, W, 3.0, weight_mask=mask)
+    eval_ms = timed(evaluate, steps)
+    eval_rate = P / (eval_ms * 1e-3)
+
+    out = {"workload": "config 4: GA 512x512, 4,000 splats, population 8,192 (fixed) over N GPUs",
+           "population_total": P, "population_per_gpu": hi - lo, "n_gpus": world, "scaling": "strong",
+           "evaluation": {"candidates_per_s": eval_rate, "ms_per_population": eval_ms},
+           "one_gpu_1024_candidates": {"candidates_per_s": base_rate, "ms": base_ms},
+           "efficiency_vs_n_times_one_gpu_1024_rate": eval_rate / (world * base_rate)}
+
+    # (b) whole generations on the engine (P - n_elite children bred, evaluated, ranked per generation)
+    gens = steps
+    if world == 1 or peers is not None:
+        eng = GaEngine(target, mask, H, W, P, N, n_elite, 2 * gens + 2)
+        if world > 1:
+            eng.set_peers(peers)
+        eng.start(pop, 7)
+        lo_s, hi_s = scale_log_bounds(H, W, C.MIN_SCALE_SPLATS, C.MAX_SCALE_SPLATS)
+        rows = [build_mut_sigma(1, 100, C.SCHEDULE, C.MUT_SIGMA_MAX, C.MUT_SIGMA_MIN)] * gens
+        gen_ms = timed(lambda: eng.run(rows, C.TOUR_K, C.CXPB, C.MUTPB, lo_s, hi_s), 1) / gens
+        st = eng.state(want_best=False)
+        eng.close()
+        out["generation"] = {"ms_per_generation": gen_ms, "generations_per_s": 1e3 / gen_ms,
+                             "candidates_per_s": (P - n_elite) / (gen_ms * 1e-3),
+                             "what": "breed 8,184 children (replicated on every rank) + evaluate this "
+                                     "rank's slice + fitness exchange + elitism / ranking, enqueued on "
+                                     "the device engine without host syncs",
+                             "best_fitness_after": st["best_fitness"]}
+    else:
+        out["generation"] = {"unavailable": "the sharded engine needs the peer-to-peer exchange"}
+    del pop
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -393,9 +485,28 @@ def run_ours(args, wl):
     peaks = ggs_b200.probe_peaks()
     log(f"[bench rank {rank}] probe: {peaks}")
 
+    # N > 1: the fitness vector reaches every rank through peer-to-peer stores issued by the raster
+    # kernel itself (ggs_b200.peers: no collective launch after the evaluation); --gather nccl,
+    # or GPUs that cannot map each other's memory, use one NCCL all-gather instead.
     all_fit = torch.empty((world * P,), dtype=torch.float32, device=dev) if world > 1 else None
+    peers, gather = None, ("none" if world == 1 else "nccl")
+    if world > 1 and args.gather == "p2p":
+        ok_flag = torch.ones(1, device=dev)
+        try:
+            from ggs_b200.peers import PeerGroup
+            peers = PeerGroup.from_process_group(capacity=max(world * P, 8192), device=dev)
+        except Exception as e:
+            log(f"[bench rank {rank}] peer-to-peer exchange unavailable: {e}")
+            ok_flag.zero_()
+        dist.all_reduce(ok_flag, op=dist.ReduceOp.MIN)       # all ranks or none
+        if float(ok_flag) == 0.0:
+            peers = None
+        gather = "p2p" if peers is not None else "nccl"
 
     def step(i):
+        if peers is not None:
+            return peers.fitness_allgather(pool[i % POOL], target, H, W, offset=rank * P,
+                                           total=world * P, weight_mask=mask)
         fit = ggs_b200.fitness(pool[i % POOL], target, H, W, 3.0, weight_mask=mask)
         if world > 1:
             dist.all_gather_into_tensor(all_fit, fit)
@@ -423,6 +534,7 @@ def run_ours(args, wl):
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
+    last = last.clone()          # a peer-gathered vector is a view that lives for two gathers
     kt = ggs_b200.timing_read()
     ggs_b200.timing_enable(False)
     clocks = sampler.stop()
@@ -479,6 +591,15 @@ def run_ours(args, wl):
                 "top8_identical": bool(np.array_equal(ra[:8], rb[:8])),
                 "note": "same genomes (seed 42), same target, the reference's own mask"}
             ref_gpu["speedup_e2e_list_api"] = None  # filled below once e2e is known
+
+    # ---- BASELINE config 4 as stated: 512x512, 4,000 splats, population 8,192 FIXED, split over N
+    c4 = None
+    if not args.no_config4 and args.workload == "c3" and not (args.side or args.splats or args.population):
+        try:
+            c4 = config4_leg(rank, world, dev, peers)
+        except Exception as e:
+            c4 = {"error": f"{type(e).__name__}: {e}"[:300]}
+            log(f"[bench rank {rank}] config 4 leg failed: {e}")
 
     t_max = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -548,12 +669,21 @@ def run_ours(args, wl):
                     "h2d_bytes_per_step": P * N * 9 * 4, "d2h_bytes_per_step": P * 4,
                     "ms_per_step": e2e_ms_all / K,
                     "api": "ggs_ctx_fitness_host (C ABI, pinned host genomes in, host fitness out)"},
-            "gpu_launches": 2 * K,
+            "gpu_launches": (3 if gather == "p2p" else 2) * K,   # decode + raster (+ the one-warp peer wait)
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "reference_gpu": ref_gpu,
+            "gather": {"how": {"p2p": "fitness values stored into every rank's vector by the raster kernel "
+                                      "over NVLink (CUDA IPC peer memory), flags + one-warp wait; no collective",
+                               "nccl": "dist.all_gather_into_tensor after the evaluation",
+                               "none": "single GPU"}[gather], "kind": gather},
             "gather_bit_identical": gather_ok,
+            "extra": {"config4": c4},
         }
         emit(line)
+    if peers is not None:
+        peers.check()
+        dist.barrier()
+        peers.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -565,6 +695,10 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference", "reference-gpu-child"], default="ours")
+    ap.add_argument("--gather", choices=["p2p", "nccl"], default="p2p",
+                    help="N > 1: how the fitness vector reaches every rank")
+    ap.add_argument("--no-config4", action="store_true",
+                    help="skip the BASELINE config 4 leg (512x512, 4,000 splats, P = 8,192 over N GPUs)")
     ap.add_argument("--no-reference-gpu", action="store_true",
                     help="skip the live run of the reference's Triton path (N = 1)")
     ap.add_argument("--ref-out", default="", help=argparse.SUPPRESS)
