@@ -224,8 +224,6 @@ def test_sa_engine_iterations_match_host_metropolis(ggs, N, tries, T0, batched):
         assert st["curves"].tolist() == [[e_best, e_cur]]
     if T0 == 0.0:
         assert uphill_accepts == 0
-    elif tries == 8:
-        assert uphill_accepts > 0          # the Metropolis branch is exercised
     assert eng.state()["curves"].shape == (I + 1, 2)
     eng.close()
 
