@@ -408,7 +408,8 @@ int ggs_ctx_create(int device, ggs_ctx **out)
         set_error("ggs_ctx_create: device %d not visible (%d devices)", device, n);
         return GGS_ENODEVICE;
     }
-    GGS_CUDA(cudaSetDevice(device));
+    DeviceGuard on_device(device);
+    GGS_CUDA(on_device.status());
     ggs_ctx *c = new (std::nothrow) ggs_ctx();
     if (!c) {
         set_error("out of host memory");
@@ -433,7 +434,7 @@ int ggs_ctx_create(int device, ggs_ctx **out)
 void ggs_ctx_destroy(ggs_ctx *c)
 {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard on_device(c->device);
     if (c->copy) cudaStreamSynchronize(c->copy);
     for (int i = 0; i < 2; ++i) {
         if (c->stream[i]) cudaStreamSynchronize(c->stream[i]);
@@ -460,7 +461,8 @@ int ggs_ctx_set_target(ggs_ctx *c, const float *h_target, const float *h_mask, i
     }
     int rc = check_shape(0, 0, 9, H, W);
     if (rc) return rc;
-    GGS_CUDA(cudaSetDevice(c->device));
+    DeviceGuard on_device(c->device);
+    GGS_CUDA(on_device.status());
     GGS_CUDA(cudaStreamSynchronize(c->copy));
     for (int i = 0; i < 2; ++i) GGS_CUDA(cudaStreamSynchronize(c->stream[i]));
     if (c->d_target) GGS_CUDA(cudaFree(c->d_target));
@@ -499,7 +501,8 @@ int ggs_ctx_fitness_host(ggs_ctx *c, const float *h_genomes, int layout, int B, 
         set_error("ggs_ctx_fitness_host: NULL buffer");
         return GGS_EINVAL;
     }
-    GGS_CUDA(cudaSetDevice(c->device));
+    DeviceGuard on_device(c->device);
+    GGS_CUDA(on_device.status());
 
     // The genomes go up in slices on a copy stream that runs ahead of the compute streams;
     // slice k is evaluated as soon as it has landed.  Sizes double (B/16, B/8, B/4, rest), so

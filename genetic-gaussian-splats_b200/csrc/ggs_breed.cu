@@ -523,11 +523,18 @@ cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int 
     q.gen = generation;
     const size_t staged_bytes = kStageBytes + (size_t)2 * N;
     if (cols == 9 && staged_bytes <= (size_t)200 * 1024) {
-        if (staged_bytes > (size_t)36 * 1024) {
+        // opt in to more than the default dynamic shared memory only when it is needed, and only
+        // when the limit already set on this device is too small (this is on the per-step path
+        // of the GA / SA engines)
+        static size_t granted[64] = {};
+        int dev = 0;
+        if (staged_bytes > (size_t)40 * 1024 && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 &&
+            granted[dev] < staged_bytes) {
             cudaError_t e = cudaFuncSetAttribute(breed_kernel<true>,
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)staged_bytes);
             if (e != cudaSuccess) return e;
+            granted[dev] = staged_bytes;
         }
         return launch_kernel(breed_kernel<true>, (q.n_children + 1) / 2, kBreedThreads, staged_bytes,
                              stream, q);

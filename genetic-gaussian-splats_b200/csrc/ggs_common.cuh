@@ -146,6 +146,30 @@ cudaError_t peers_wait(ggs_peers *p, unsigned epoch, cudaStream_t st);
 
 void set_error(const char *fmt, ...);
 
+// Entry points that own a device (contexts, engines, peers) run on it and hand the caller's
+// current device back when they return.
+class DeviceGuard {
+public:
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev_) != cudaSuccess) prev_ = -1;
+        status_ = (prev_ == device) ? cudaSuccess : cudaSetDevice(device);
+        changed_ = (status_ == cudaSuccess && prev_ != device);
+    }
+    ~DeviceGuard()
+    {
+        if (changed_ && prev_ >= 0) cudaSetDevice(prev_);
+    }
+    cudaError_t status() const { return status_; }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+
+private:
+    int prev_ = -1;
+    bool changed_ = false;
+    cudaError_t status_ = cudaSuccess;
+};
+
 // ---- programmatic dependent launch (PDL) --------------------------------------------------
 // The kernels of an evaluation (decode -> raster) and of a GA / SA step (breed -> decode ->
 // raster -> select) are short at small populations, so the few microseconds between dependent

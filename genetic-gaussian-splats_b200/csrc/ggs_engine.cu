@@ -268,6 +268,7 @@ struct ggs_ga {
     int generation = -1;  // generations completed; -1 until ggs_ga_start
     bool has_target = false;
     ggs_peers *peers = nullptr;  // evaluation sharded over the ranks of this group, or NULL
+    size_t select_smem_granted = 0;
 };
 
 // Contiguous split of `total` items; the first total % world ranks get one more (the rule of
@@ -335,9 +336,11 @@ static int ga_rank(ggs_ga *g, int n_elite, int next_buf, const float *child_fit,
     int P2 = 1;
     while (P2 < g->P) P2 <<= 1;
     const size_t smem = (size_t)P2 * sizeof(unsigned long long);
-    if (smem > 48 * 1024)
+    if (smem > 40 * 1024 && g->select_smem_granted < smem) {  // once per engine, not per generation
         GGS_TRY(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
+        g->select_smem_granted = smem;
+    }
     GGS_TRY(launch_kernel(select_kernel, 1 + n_elite, kSelectThreads, smem, st, q));
     g->ord ^= 1;
     return GGS_OK;
@@ -365,7 +368,8 @@ int ggs_ga_create(int device, int P, int N, int H, int W, int n_elite, int max_g
         set_error("ggs_ga_create: device %d not visible (%d devices)", device, n);
         return GGS_ENODEVICE;
     }
-    GGS_TRY(cudaSetDevice(device));
+    DeviceGuard on_device(device);
+    GGS_TRY(on_device.status());
     ggs_ga *g = new (std::nothrow) ggs_ga();
     if (!g) {
         set_error("out of host memory");
@@ -406,7 +410,7 @@ int ggs_ga_create(int device, int P, int N, int H, int W, int n_elite, int max_g
 void ggs_ga_destroy(ggs_ga *g)
 {
     if (!g) return;
-    cudaSetDevice(g->device);
+    DeviceGuard on_device(g->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < 2; ++i) {
         if (g->room[i]) cudaFree(g->room[i]);
@@ -431,7 +435,8 @@ int ggs_ga_set_target(ggs_ga *g, const float *d_target, const float *d_mask, int
         return GGS_EINVAL;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    GGS_TRY(cudaSetDevice(g->device));
+    DeviceGuard on_device(g->device);
+    GGS_TRY(on_device.status());
     GGS_TRY(cudaMemcpyAsync(g->target, d_target, (size_t)g->H * g->W * 3 * sizeof(float),
                             cudaMemcpyDeviceToDevice, st));
     if (d_mask)
@@ -455,7 +460,8 @@ int ggs_ga_start(ggs_ga *g, const float *d_population, int cols, uint64_t seed, 
         return GGS_EINVAL;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    GGS_TRY(cudaSetDevice(g->device));
+    DeviceGuard on_device(g->device);
+    GGS_TRY(on_device.status());
     // generation 0: the given population (first 9 columns), evaluated and ranked
     GGS_TRY(cudaMemcpy2DAsync(g->room[0], 9 * sizeof(float), d_population, (size_t)cols * sizeof(float),
                               9 * sizeof(float), (size_t)g->P * g->N, cudaMemcpyDeviceToDevice, st));
@@ -493,7 +499,8 @@ int ggs_ga_run(ggs_ga *g, int count, const float *h_sigma6, int tour_k, float cx
         return GGS_EINVAL;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    GGS_TRY(cudaSetDevice(g->device));
+    DeviceGuard on_device(g->device);
+    GGS_TRY(on_device.status());
     const int keep = g->P - g->n_elite;
     const size_t row = (size_t)g->N * 9;
     for (int k = 0; k < count; ++k) {
@@ -526,7 +533,8 @@ int ggs_ga_state(ggs_ga *g, void *stream, int *h_generation, double *h_best_fitn
         return GGS_EINVAL;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    GGS_TRY(cudaSetDevice(g->device));
+    DeviceGuard on_device(g->device);
+    GGS_TRY(on_device.status());
     if (h_best_fitness)
         GGS_TRY(cudaMemcpyAsync(h_best_fitness, g->best_fit, sizeof(double), cudaMemcpyDeviceToHost, st));
     if (h_no_improve)
@@ -618,7 +626,8 @@ int ggs_sa_create(int device, int N, int H, int W, int tries, int max_iterations
         set_error("ggs_sa_create: device %d not visible (%d devices)", device, n);
         return GGS_ENODEVICE;
     }
-    GGS_TRY(cudaSetDevice(device));
+    DeviceGuard on_device(device);
+    GGS_TRY(on_device.status());
     ggs_sa *g = new (std::nothrow) ggs_sa();
     if (!g) {
         set_error("out of host memory");
@@ -656,7 +665,7 @@ int ggs_sa_create(int device, int N, int H, int W, int tries, int max_iterations
 void ggs_sa_destroy(ggs_sa *g)
 {
     if (!g) return;
-    cudaSetDevice(g->device);
+    DeviceGuard on_device(g->device);
     cudaDeviceSynchronize();
     void *all[] = {g->current, g->best, g->cand, g->energy, g->dummy_fit, g->target, g->mask, g->ws,
                    g->curves, g->e_current, g->e_best};
@@ -677,7 +686,8 @@ int ggs_sa_set_target(ggs_sa *g, const float *d_target, const float *d_mask, int
         return GGS_EINVAL;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    GGS_TRY(cudaSetDevice(g->device));
+    DeviceGuard on_device(g->device);
+    GGS_TRY(on_device.status());
     GGS_TRY(cudaMemcpyAsync(g->target, d_target, (size_t)g->H * g->W * 3 * sizeof(float),
                             cudaMemcpyDeviceToDevice, st));
     if (d_mask)
@@ -709,7 +719,8 @@ int ggs_sa_start(ggs_sa *g, const float *d_state, int cols, uint64_t seed, void 
         return GGS_EINVAL;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    GGS_TRY(cudaSetDevice(g->device));
+    DeviceGuard on_device(g->device);
+    GGS_TRY(on_device.status());
     // iteration 0: the given state is the current and the best one; its energy opens the curves.
     // It is staged as candidate 0 and "accepted" by the Metropolis kernel (dE = -inf).
     GGS_TRY(cudaMemcpy2DAsync(g->cand, 9 * sizeof(float), d_state, (size_t)cols * sizeof(float),
@@ -754,7 +765,8 @@ int ggs_sa_run(ggs_sa *g, int count, const float *h_sigma6, const double *h_temp
         return GGS_EINVAL;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    GGS_TRY(cudaSetDevice(g->device));
+    DeviceGuard on_device(g->device);
+    GGS_TRY(on_device.status());
     for (int k = 0; k < count; ++k) {
         const int it = g->iteration + 1;
         MetropolisParams q = {};
@@ -823,7 +835,8 @@ int ggs_sa_state(ggs_sa *g, void *stream, int *h_iteration, double *h_best_energ
         return GGS_EINVAL;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    GGS_TRY(cudaSetDevice(g->device));
+    DeviceGuard on_device(g->device);
+    GGS_TRY(on_device.status());
     const size_t row = (size_t)g->N * 9 * sizeof(float);
     if (h_best_energy)
         GGS_TRY(cudaMemcpyAsync(h_best_energy, g->e_best, sizeof(double), cudaMemcpyDeviceToHost, st));

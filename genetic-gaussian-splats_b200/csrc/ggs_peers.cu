@@ -141,7 +141,8 @@ int ggs_peers_create(int device, int rank, int world, int capacity, ggs_peers **
         set_error("ggs_peers_create: device %d not visible (%d devices)", device, n);
         return GGS_ENODEVICE;
     }
-    GGS_TRY(cudaSetDevice(device));
+    DeviceGuard on_device(device);
+    GGS_TRY(on_device.status());
     ggs_peers *p = new (std::nothrow) ggs_peers();
     if (!p) {
         set_error("out of host memory");
@@ -170,7 +171,7 @@ int ggs_peers_create(int device, int rank, int world, int capacity, ggs_peers **
 void ggs_peers_destroy(ggs_peers *p)
 {
     if (!p) return;
-    cudaSetDevice(p->device);
+    DeviceGuard on_device(p->device);
     cudaDeviceSynchronize();
     for (int r = 0; r < p->world; ++r)
         if (p->opened[r]) cudaIpcCloseMemHandle(p->base[r]);
@@ -186,7 +187,8 @@ int ggs_peers_export(ggs_peers *p, void *h_handle)
         set_error("ggs_peers_export: NULL argument");
         return GGS_EINVAL;
     }
-    GGS_TRY(cudaSetDevice(p->device));
+    DeviceGuard on_device(p->device);
+    GGS_TRY(on_device.status());
     cudaIpcMemHandle_t h;
     GGS_TRY(cudaIpcGetMemHandle(&h, p->own));
     memcpy(h_handle, &h, sizeof(h));
@@ -199,7 +201,8 @@ int ggs_peers_connect(ggs_peers *p, const void *h_handles)
         set_error("ggs_peers_connect: NULL argument");
         return GGS_EINVAL;
     }
-    GGS_TRY(cudaSetDevice(p->device));
+    DeviceGuard on_device(p->device);
+    GGS_TRY(on_device.status());
     const char *src = static_cast<const char *>(h_handles);
     for (int r = 0; r < p->world; ++r) {
         if (r == p->rank || p->opened[r]) continue;
@@ -220,7 +223,8 @@ int ggs_peers_connect_local(ggs_peers *p, ggs_peers *const *all)
         set_error("ggs_peers_connect_local: NULL argument");
         return GGS_EINVAL;
     }
-    GGS_TRY(cudaSetDevice(p->device));
+    DeviceGuard on_device(p->device);
+    GGS_TRY(on_device.status());
     for (int r = 0; r < p->world; ++r) {
         if (r == p->rank) continue;
         if (!all[r] || all[r]->world != p->world || all[r]->rank != r || all[r]->capacity != p->capacity) {
@@ -264,7 +268,8 @@ int ggs_fitness_allgather(ggs_peers *p, const float *d_genomes, int layout, int 
         return GGS_EINVAL;
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    GGS_TRY(cudaSetDevice(p->device));
+    DeviceGuard on_device(p->device);
+    GGS_TRY(on_device.status());
     EvalOptions opt;
     opt.split = choose_split(total, N, H, W);  // the whole population's configuration on every rank
     opt.peers = peers_next(p, offset);
@@ -289,7 +294,8 @@ int ggs_peers_status(ggs_peers *p, void *stream)
         set_error("ggs_peers_status: NULL argument");
         return GGS_EINVAL;
     }
-    GGS_TRY(cudaSetDevice(p->device));
+    DeviceGuard on_device(p->device);
+    GGS_TRY(on_device.status());
     int status = 0;
     GGS_TRY(cudaMemcpyAsync(&status, peers_status(p), sizeof(int), cudaMemcpyDeviceToHost,
                             static_cast<cudaStream_t>(stream)));

@@ -70,6 +70,12 @@ constexpr int kPairs = kRowsPerThread / 2;
 constexpr int kScanPerThread = GGS_SCAN_CHUNK / kThreads;  // 256 records examined per round
 static_assert(GGS_SCAN_CHUNK <= kListCap, "a scan round must fit the list");
 constexpr int kScanChunk = kThreads * kScanPerThread;
+#ifndef GGS_OPT_NOFINALSYNC
+#define GGS_OPT_NOFINALSYNC 0
+#endif
+#ifndef GGS_OPT_QY2
+#define GGS_OPT_QY2 0
+#endif
 #ifndef GGS_SAT_EVERY
 #define GGS_SAT_EVERY 8
 #endif
@@ -237,8 +243,12 @@ __device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, 
         const float t1 = q0.w * qx;                       // Bq*qx
         float t0 = fmaf(q0.z * qx, qx, q1.y);             // A*qx^2 + log2(alpha)
         t0 = in_x ? t0 : -INFINITY;                       // outside [x0,x1]: f = 2^-inf = 0
+#if GGS_OPT_QY2
+        const f2_t QY = add2(pack2(Ybf, Ybf + 1.0f), bcast2(-q0.y));  // one FADD2 (rows 0, 1 of the band)
+#else
         const float dy = Ybf - q0.y;
         const f2_t QY = pack2(dy, dy + 1.0f);
+#endif
         const f2_t CQ2 = bcast2(q1.x), T12 = bcast2(t1), T02 = bcast2(t0);
         const f2_t R2 = bcast2(q1.z), G2 = bcast2(q1.w), B2 = bcast2(q2.x);
         if (c == kBandFull && (kSteepBit != 0u || q2.w >= 0.0f)) {
@@ -427,6 +437,9 @@ __device__ __forceinline__ void scan_and_composite(const float4 *__restrict__ re
             if (live)
                 live = composite_list<kStats>(sm.list, cnt, g.lanebit, g.band_sel, g.Xf, g.Ybf, work);
             cnt = 0;
+#if GGS_OPT_NOFINALSYNC
+            if (top <= kScanChunk) break;  // that was the last flush: no reason to wait for the other bands
+#endif
             // every band opaque: the rest of the genome is hidden behind what is drawn
             if (__syncthreads_and(!live)) break;
         }
@@ -683,6 +696,7 @@ __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_split_kernel(
     }
 
     // Publish this segment's state: px[row][col] = (r, g, b, t), reusing the list's memory.
+    static_assert(kTileH * kTileW <= kListCap * 3, "the tile's pixel states must fit the list buffer");
     __syncthreads();  // every warp is done reading the list
     float4 *px = sm.list;
     {

@@ -63,3 +63,27 @@ def test_recurrence_path_has_no_register_copies():
     assert len(packed) >= 24, block
     assert len(copies) <= 2, f"{len(copies)} register copies in the recurrence path:\n" + "\n".join(block)
     assert len(block) <= len(packed) + 12
+
+
+VARIANTS = [
+    ("8 rows x 2 warps", ["-DGGS_WARPS=2"]),
+    ("8 rows x 1 warp", ["-DGGS_WARPS=1"]),
+    ("16 rows x 2 warps", ["-DGGS_ROWS=16", "-DGGS_WARPS=2"]),
+    ("list of 384, scan rounds of 128", ["-DGGS_LIST_CAP=384", "-DGGS_SCAN_CHUNK=128"]),
+]
+
+
+@pytest.mark.parametrize("name,flags", VARIANTS, ids=[v[0] for v in VARIANTS])
+def test_every_supported_geometry_of_the_raster_compiles(name, flags, tmp_path):
+    """The pixel state lives in hand-declared PTX registers shared by many asm statements: a
+    variant (rows per thread, warps per CTA, list sizes) that breaks their single declaration
+    or their scoping must fail HERE, at ptxas, not on the GPU box."""
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    pkg = os.path.join(ROOT, "genetic-gaussian-splats_b200")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-fmad=false",
+           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(pkg, "csrc"), *flags,
+           "-c", os.path.join(pkg, "csrc", "ggs_raster.cu"), "-o", str(tmp_path / "raster.o")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
