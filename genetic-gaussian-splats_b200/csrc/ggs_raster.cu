@@ -71,7 +71,10 @@ constexpr int kScanPerThread = GGS_SCAN_CHUNK / kThreads;  // 256 records examin
 static_assert(GGS_SCAN_CHUNK <= kListCap, "a scan round must fit the list");
 constexpr int kScanChunk = kThreads * kScanPerThread;
 #ifndef GGS_OPT_NOFINALSYNC
-#define GGS_OPT_NOFINALSYNC 0
+#define GGS_OPT_NOFINALSYNC 1   // neutral at config 3, 4 % of a small launch
+#endif
+#ifndef GGS_EPI_BATCH
+#define GGS_EPI_BATCH 4   // rows whose fitness inputs are loaded together in the epilogue (8 spills the pixel state)
 #endif
 #ifndef GGS_OPT_QY2
 #define GGS_OPT_QY2 0
@@ -499,17 +502,37 @@ __device__ __forceinline__ int build_list_fused(const float *__restrict__ gb, in
     return cnt;
 }
 
+// The fitness inputs of one pixel: target colour and weight (fitness.py:16-31).  Issued for all of
+// a thread's pixels BEFORE any of them is used, so the epilogue pays one L2 round trip, not one
+// per row (measured: a third of a small launch's time went into eight serial round trips).
+struct PixelInputs {
+    float tr, tg, tb, w;
+};
+
+__device__ __forceinline__ PixelInputs load_inputs(const RasterArgs &a, int X, int Y)
+{
+    PixelInputs in = {0.0f, 0.0f, 0.0f, 1.0f};
+    if (a.target != nullptr && X < a.W && Y < a.H) {
+        const int64_t p = (int64_t)Y * a.W + X;
+        in.tr = __ldg(a.target + 3 * p + 0);
+        in.tg = __ldg(a.target + 3 * p + 1);
+        in.tb = __ldg(a.target + 3 * p + 2);
+        if (a.mode != GGS_MODE_PLAIN) in.w = __ldg(a.mask + p);
+    }
+    return in;
+}
+
 // One finished pixel: background through the remaining transmittance (render.py:236-237), clamp
 // (render.py:252), optional image store, squared error (fitness.py:16-31).
 __device__ __forceinline__ void emit_pixel(const RasterArgs &a, int b, int X, int Y, float pr, float pg,
-                                           float pb, float pt, float &num, float &den)
+                                           float pb, float pt, const PixelInputs &in, float &num,
+                                           float &den)
 {
     const float cr = clamp01(fmaf(pt, a.bg_r, pr));
     const float cg = clamp01(fmaf(pt, a.bg_g, pg));
     const float cb = clamp01(fmaf(pt, a.bg_b, pb));
-    const int64_t p = (int64_t)Y * a.W + X;
     if (a.images != nullptr) {
-        const int64_t at = ((int64_t)b * a.H * a.W + p) * 3;
+        const int64_t at = (((int64_t)b * a.H + Y) * a.W + X) * 3;
         if (a.image_u8) {  // (img * 255).astype(uint8): truncation (utils.py:57)
             unsigned char *o = reinterpret_cast<unsigned char *>(a.images) + at;
             o[0] = (unsigned char)(cr * 255.0f);
@@ -523,14 +546,8 @@ __device__ __forceinline__ void emit_pixel(const RasterArgs &a, int b, int X, in
         }
     }
     if (a.target != nullptr) {
-        const float dr = cr - __ldg(a.target + 3 * p + 0);
-        const float dg = cg - __ldg(a.target + 3 * p + 1);
-        const float db = cb - __ldg(a.target + 3 * p + 2);
-        float w = 1.0f;
-        if (a.mode == GGS_MODE_MASK)
-            w = __ldg(a.mask + p);
-        else if (a.mode == GGS_MODE_BOOST)
-            w = fmaf(a.beta, clamp01(__ldg(a.mask + p)), 1.0f);
+        const float dr = cr - in.tr, dg = cg - in.tg, db = cb - in.tb;
+        const float w = (a.mode == GGS_MODE_BOOST) ? fmaf(a.beta, clamp01(in.w), 1.0f) : in.w;
         num += (dr * dr) * w + (dg * dg) * w + (db * db) * w;
         den += w;
     }
@@ -647,14 +664,34 @@ __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_kernel(const 
     float num = 0.0f, den = 0.0f;
     float prr[kPairs][2], pgg[kPairs][2], pbb[kPairs][2], ptt[kPairs][2];
 #define GGS_READ_ALL(k) GGS_PX_READ(k, prr[k], pgg[k], pbb[k], ptt[k])
+#if GGS_EPI_BATCH >= GGS_ROWS
+    PixelInputs in[kRowsPerThread];
+#pragma unroll
+    for (int i = 0; i < kRowsPerThread; ++i) in[i] = load_inputs(a, g.X, g.Yb + i);
     GGS_PAIRS(GGS_READ_ALL)
 #pragma unroll
     for (int i = 0; i < kRowsPerThread; ++i) {
         const int Y = g.Yb + i;
         if (g.X < a.W && Y < a.H)
             emit_pixel(a, g.b, g.X, Y, prr[i >> 1][i & 1], pgg[i >> 1][i & 1], pbb[i >> 1][i & 1],
-                       ptt[i >> 1][i & 1], num, den);
+                       ptt[i >> 1][i & 1], in[i], num, den);
     }
+#else
+    GGS_PAIRS(GGS_READ_ALL)
+#pragma unroll
+    for (int i0 = 0; i0 < kRowsPerThread; i0 += GGS_EPI_BATCH) {
+        PixelInputs in[GGS_EPI_BATCH];
+#pragma unroll
+        for (int i = 0; i < GGS_EPI_BATCH; ++i) in[i] = load_inputs(a, g.X, g.Yb + i0 + i);
+#pragma unroll
+        for (int j = 0; j < GGS_EPI_BATCH; ++j) {
+            const int i = i0 + j, Y = g.Yb + i;
+            if (g.X < a.W && Y < a.H)
+                emit_pixel(a, g.b, g.X, Y, prr[i >> 1][i & 1], pgg[i >> 1][i & 1], pbb[i >> 1][i & 1],
+                           ptt[i >> 1][i & 1], in[j], num, den);
+        }
+    }
+#endif
     if (kStats && lane == 0) {
         // pixel-splat pairs actually evaluated: 64 lanes-rows per blended row pair
         atomicAdd(a.stats + 0, (unsigned long long)work[0]);
@@ -716,16 +753,26 @@ __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_split_kernel(
     const int rows_per = kTileH / K;
     for (int p = tid; p < rows_per * kTileW; p += kThreads) {
         const int row = k * rows_per + p / kTileW, col = p % kTileW;
-        float cr = 0.0f, cgr = 0.0f, cb = 0.0f, t = 1.0f;
-        for (int s = K - 1; s >= 0; --s) {
-            const float4 v = cluster.map_shared_rank(px, s)[row * kTileW + col];
-            cr = fmaf(t, v.x, cr);
-            cgr = fmaf(t, v.y, cgr);
-            cb = fmaf(t, v.z, cb);
-            t *= v.w;
-        }
         const int X = g.X0 + col, Y = g.Y0 + row;
-        if (X < a.W && Y < a.H) emit_pixel(a, g.b, X, Y, cr, cgr, cb, t, num, den);
+        // every load of this pixel -- the K remote states and the fitness inputs -- is issued
+        // before the first use: one trip over the cluster network and one to L2, not K + 1
+        float4 v[kMaxSplit];
+#pragma unroll
+        for (int s = 0; s < kMaxSplit; ++s)
+            v[s] = (s < K) ? cluster.map_shared_rank(px, s)[row * kTileW + col]
+                           : make_float4(0.0f, 0.0f, 0.0f, 1.0f);  // the identity of the fold
+        const PixelInputs in = load_inputs(a, X, Y);
+        float cr = 0.0f, cgr = 0.0f, cb = 0.0f, t = 1.0f;
+#pragma unroll
+        for (int s = kMaxSplit - 1; s >= 0; --s) {
+            if (s < K) {
+                cr = fmaf(t, v[s].x, cr);
+                cgr = fmaf(t, v[s].y, cgr);
+                cb = fmaf(t, v[s].z, cb);
+                t *= v[s].w;
+            }
+        }
+        if (X < a.W && Y < a.H) emit_pixel(a, g.b, X, Y, cr, cgr, cb, t, in, num, den);
     }
     cluster.sync();  // nobody leaves while a neighbour still reads its shared memory
     if (a.target == nullptr) return;

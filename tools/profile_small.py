@@ -7,7 +7,9 @@ import torch
 import ggs_b200
 from ggs_b200 import synth
 ggs_b200.set_option("fuse", 0)
-for side, N, B, split in ((128, 100, 32, 1), (256, 500, 8, 1), (256, 500, 1, 8)):
+import os
+CASES = {"c1": (128, 100, 32, 1), "c2": (256, 500, 8, 2), "b1": (256, 500, 1, 8)}
+for side, N, B, split in [CASES[os.environ.get("CASE", "c1")]]:
     H = W = side
     target = torch.from_numpy(synth.synthetic_target_np(H, W, 0)).cuda()
     g = torch.from_numpy(synth.new_population_np(B, N, H, W, seed=1)).cuda()
