@@ -131,15 +131,49 @@ __device__ __forceinline__ f2_t add2(f2_t a, f2_t b)
     return d;
 }
 
-// ---- pixel state: named PTX registers ggs_{r,g,b,t}<pair> -------------------------------------
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b)
+{
+    f2_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f2_t sub2(f2_t a, f2_t b)
+{
+    f2_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// ---- pixel state ----------------------------------------------------------------------------
 // Pair k of a thread holds rows (2k, 2k+1) of its column: accumulated colour (premultiplied,
 // front to back) and transmittance.  GGS_PAIRS(M) expands M(0) ... M(kPairs-1).
+//
+// GGS_NAMED_REGS = 1 (default): the state lives in PTX registers declared ONCE per kernel
+// (ggs_{r,g,b,t}<pair>, ggs_F, ggs_G) that only in-place PTX touches; as C++ values ptxas renamed
+// the 64-bit accumulators out of place in most builds and paid ~20 MOVs per splat
+// (tests/test_cpu_sass.py guards this).  The declaration has to stay in the kernel's entry block
+// and every user has to be inlined into that kernel.
+// GGS_NAMED_REGS = 0: the same operations on ordinary C++ values (struct PixelState), kept so
+// that a toolchain that rejects or mis-scopes the hand-declared registers cannot brick the
+// raster; tests/test_cpu_sass.py compiles it.
+#ifndef GGS_NAMED_REGS
+#define GGS_NAMED_REGS 1
+#endif
 #if GGS_ROWS == 8
-#define GGS_PX_DECLARE() asm volatile(".reg .b64 ggs_r<4>, ggs_g<4>, ggs_b<4>, ggs_t<4>, ggs_F, ggs_G;")
 #define GGS_PAIRS(M) M(0) M(1) M(2) M(3)
 #else
-#define GGS_PX_DECLARE() asm volatile(".reg .b64 ggs_r<8>, ggs_g<8>, ggs_b<8>, ggs_t<8>, ggs_F, ggs_G;")
 #define GGS_PAIRS(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7)
+#endif
+#if GGS_NAMED_REGS
+struct PixelState {};
+#if GGS_ROWS == 8
+#define GGS_PX_DECLARE()                                                                       \
+    asm volatile(".reg .b64 ggs_r<4>, ggs_g<4>, ggs_b<4>, ggs_t<4>, ggs_F, ggs_G;");           \
+    PixelState px
+#else
+#define GGS_PX_DECLARE()                                                                       \
+    asm volatile(".reg .b64 ggs_r<8>, ggs_g<8>, ggs_b<8>, ggs_t<8>, ggs_F, ggs_G;");           \
+    PixelState px
 #endif
 #define GGS_PX_INIT(k, ta_, tb_)                                                          \
     asm volatile("mov.b64 ggs_r" #k ", 0;\n\tmov.b64 ggs_g" #k ", 0;\n\tmov.b64 ggs_b" #k   \
@@ -164,6 +198,35 @@ __device__ __forceinline__ f2_t add2(f2_t a, f2_t b)
                  ";\n\tmov.b64 {%4, %5}, ggs_b" #k ";\n\tmov.b64 {%6, %7}, ggs_t" #k ";"   \
                  : "=f"(r_[0]), "=f"(r_[1]), "=f"(g_[0]), "=f"(g_[1]), "=f"(b_[0]),       \
                    "=f"(b_[1]), "=f"(t_[0]), "=f"(t_[1]));
+#else
+struct PixelState {
+    f2_t r[GGS_ROWS / 2], g[GGS_ROWS / 2], b[GGS_ROWS / 2], t[GGS_ROWS / 2], F, G;
+};
+#define GGS_PX_DECLARE() PixelState px
+#define GGS_PX_INIT(k, ta_, tb_) \
+    px.r[k] = 0ull;              \
+    px.g[k] = 0ull;              \
+    px.b[k] = 0ull;              \
+    px.t[k] = pack2(ta_, tb_);
+#define GGS_SET_F(f0_, f1_) px.F = pack2(f0_, f1_);
+#define GGS_SET_G(g0_, g1_) px.G = pack2(g0_, g1_);
+#define GGS_STEP_F() px.F = mul2(px.F, px.G);
+#define GGS_STEP_G(H_) px.G = mul2(px.G, H_);
+#define GGS_PX_BLEND(k)                         \
+    {                                           \
+        const f2_t w_ = mul2(px.F, px.t[k]);    \
+        px.r[k] = fma2(w_, R2, px.r[k]);        \
+        px.g[k] = fma2(w_, G2, px.g[k]);        \
+        px.b[k] = fma2(w_, B2, px.b[k]);        \
+        px.t[k] = sub2(px.t[k], w_);            \
+    }
+#define GGS_PX_READ_T(k, a_, b_) unpack2(px.t[k], a_, b_);
+#define GGS_PX_READ(k, r_, g_, b_, t_)  \
+    unpack2(px.r[k], r_[0], r_[1]);     \
+    unpack2(px.g[k], g_[0], g_[1]);     \
+    unpack2(px.b[k], b_[0], b_[1]);     \
+    unpack2(px.t[k], t_[0], t_[1]);
+#endif
 
 // Staged record (shared memory, 3 x float4), specialised for the tile by the staging thread:
 //   q0 = cx, cy, A, Bq      q1 = Cq, la, r, g      q2 = b, lane mask, row code, h
@@ -216,7 +279,7 @@ __device__ __forceinline__ unsigned lane_mask(int x0, int x1, int X0)
 // back can change a pixel by more than kOpaque (colours are in [0,1]), so the warp stops
 // (returns false).  Checked every kSatEvery list entries with one warp vote.
 template <bool kStats>
-__device__ __forceinline__ bool composite_list(const float4 *__restrict__ list, int cnt,
+__device__ __forceinline__ bool composite_list(PixelState &px, const float4 *__restrict__ list, int cnt,
                                                unsigned lanebit, unsigned band_sel, float Xf,
                                                float Ybf, unsigned (&work)[2])
 {
@@ -374,7 +437,7 @@ struct RasterSmem {
 // to be composited, one list entry per thread, so the staging code runs ceil(cnt / kThreads)
 // times per flush instead of once per (round, slot) with a few lanes active.
 template <bool kStats>
-__device__ __forceinline__ void scan_and_composite(const float4 *__restrict__ recb,
+__device__ __forceinline__ void scan_and_composite(PixelState &px, const float4 *__restrict__ recb,
                                                    const uint2 *__restrict__ boxb, int n,
                                                    const TileGeom &g, const RasterSmem &sm, int tid, int lane,
                                                    int warp, unsigned (&work)[2])
@@ -438,7 +501,7 @@ __device__ __forceinline__ void scan_and_composite(const float4 *__restrict__ re
             cp_async_wait_all();
             __syncthreads();
             if (live)
-                live = composite_list<kStats>(sm.list, cnt, g.lanebit, g.band_sel, g.Xf, g.Ybf, work);
+                live = composite_list<kStats>(px, sm.list, cnt, g.lanebit, g.band_sel, g.Xf, g.Ybf, work);
             cnt = 0;
 #if GGS_OPT_NOFINALSYNC
             if (top <= kScanChunk) break;  // that was the last flush: no reason to wait for the other bands
@@ -658,7 +721,7 @@ __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_kernel(const 
     prefetch_tile_inputs(a, g, tid);  // inputs nobody ahead of us writes
     pdl_wait();  // the decode launch ahead of us has completed; nothing above reads its output
     pdl_trigger();
-    scan_and_composite<kStats>(a.rec + (int64_t)g.b * a.N * 3, a.aabb + (int64_t)g.b * a.N, a.N, g, sm,
+    scan_and_composite<kStats>(px, a.rec + (int64_t)g.b * a.N * 3, a.aabb + (int64_t)g.b * a.N, a.N, g, sm,
                                tid, lane, warp, work);
 
     float num = 0.0f, den = 0.0f;
@@ -724,24 +787,24 @@ __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_split_kernel(
     pdl_wait();
     pdl_trigger();
     if (kDecode == 0) {
-        scan_and_composite<false>(a.rec + ((int64_t)g.b * a.N + i_lo) * 3,
+        scan_and_composite<false>(px, a.rec + ((int64_t)g.b * a.N + i_lo) * 3,
                                   a.aabb + (int64_t)g.b * a.N + i_lo, n, g, sm, tid, lane, warp, work);
     } else {
         const int cnt = build_list_fused<kDecode == 1>(a.genomes + (int64_t)g.b * a.N * a.cols, a.cols,
                                                        i_lo, n, a.H, a.W, a.k_sigma, g, sm, tid, lane, warp);
-        composite_list<false>(sm.list, cnt, g.lanebit, g.band_sel, g.Xf, g.Ybf, work);
+        composite_list<false>(px, sm.list, cnt, g.lanebit, g.band_sel, g.Xf, g.Ybf, work);
     }
 
-    // Publish this segment's state: px[row][col] = (r, g, b, t), reusing the list's memory.
+    // Publish this segment's state: exch[row][col] = (r, g, b, t), reusing the list's memory.
     static_assert(kTileH * kTileW <= kListCap * 3, "the tile's pixel states must fit the list buffer");
     __syncthreads();  // every warp is done reading the list
-    float4 *px = sm.list;
+    float4 *exch = sm.list;
     {
         float prr[kPairs][2], pgg[kPairs][2], pbb[kPairs][2], ptt[kPairs][2];
         GGS_PAIRS(GGS_READ_ALL)
 #pragma unroll
         for (int i = 0; i < kRowsPerThread; ++i)
-            px[(warp * kRowsPerThread + i) * kTileW + lane] =
+            exch[(warp * kRowsPerThread + i) * kTileW + lane] =
                 make_float4(prr[i >> 1][i & 1], pgg[i >> 1][i & 1], pbb[i >> 1][i & 1], ptt[i >> 1][i & 1]);
     }
     cg::cluster_group cluster = cg::this_cluster();
@@ -759,7 +822,7 @@ __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_split_kernel(
         float4 v[kMaxSplit];
 #pragma unroll
         for (int s = 0; s < kMaxSplit; ++s)
-            v[s] = (s < K) ? cluster.map_shared_rank(px, s)[row * kTileW + col]
+            v[s] = (s < K) ? cluster.map_shared_rank(exch, s)[row * kTileW + col]
                            : make_float4(0.0f, 0.0f, 0.0f, 1.0f);  // the identity of the fold
         const PixelInputs in = load_inputs(a, X, Y);
         float cr = 0.0f, cgr = 0.0f, cb = 0.0f, t = 1.0f;

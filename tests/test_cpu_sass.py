@@ -70,6 +70,7 @@ VARIANTS = [
     ("8 rows x 1 warp", ["-DGGS_WARPS=1"]),
     ("16 rows x 2 warps", ["-DGGS_ROWS=16", "-DGGS_WARPS=2"]),
     ("list of 384, scan rounds of 128", ["-DGGS_LIST_CAP=384", "-DGGS_SCAN_CHUNK=128"]),
+    ("pixel state as C++ values (fallback for the named PTX registers)", ["-DGGS_NAMED_REGS=0"]),
 ]
 
 
