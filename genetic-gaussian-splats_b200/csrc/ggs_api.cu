@@ -63,8 +63,15 @@ int choose_split(int B, int N, int H, int W)
 {
     const int forced = options().split;
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
+    // Measured on the B200 (profiles/r02_small_batch.txt): the split pays while the grid leaves
+    // most SMs with less than one CTA per scheduler -- B * tiles * split within HALF a wave --
+    // (one SA try at 256x256: 25.7 -> 13.8 us at split 8) and stops paying at 512 CTAs (configs 1
+    // and 2: split 1 is the fastest); and it must not be used on deep genomes, whose bands go
+    // opaque early: the segments cannot see each other's saturation (512x512 / 4,000 splats, one
+    // frame: 40.8 us at split 1, 68 us at split 4).
+    if (N > 1536) return 1;
     const int64_t ctas = (int64_t)B * tiles_x(W) * tiles_y(H);
-    const int slots = wave_slots();
+    const int slots = wave_slots() / 2;
     int k = 1;
     while (k < kMaxSplit && ctas * (k * 2) <= slots && (N + 2 * k - 1) / (2 * k) >= 16) k *= 2;
     return k;

@@ -286,8 +286,8 @@ int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, 
              int mode, float beta, float *d_fitness, void *d_images, int image_u8,
              void *d_workspace, size_t workspace_bytes_given, cudaStream_t stream,
              const EvalOptions &opt = EvalOptions());
-// Largest split (1, 2, 4, 8) that keeps B * tiles * split CTAs within one wave of the device and
-// every genome segment worth a CTA; the policy behind split = 0.
+// Largest split (1, 2, 4, 8) that keeps B * tiles * split CTAs within half a wave of the device
+// and every genome segment worth a CTA, 1 for deep genomes; the policy behind split = 0.
 int choose_split(int B, int N, int H, int W);
 
 }  // namespace ggs

@@ -96,13 +96,16 @@ def test_a_given_split_is_deterministic_and_independent_of_the_call_boundaries(g
 
 
 def test_automatic_split_policy(ggs):
-    # one wave of 8 CTAs per SM; segments of at least 16 splats
+    # half a wave (4 CTAs per SM); segments of at least 16 splats; never on deep genomes
     import ggs_b200
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    slots = 8 * sms
+    slots = 4 * sms
     assert ggs.choose_split(1024, 1000, 256, 256) == 1          # config 3: throughput path
     assert ggs.choose_split(1, 500, 256, 256) == 8              # one SA try: 64 tiles x 8
-    for B, N, side in ((32, 100, 128), (8, 500, 256), (4, 20, 64), (3, 1000, 512)):
+    assert ggs.choose_split(32, 100, 128, 128) == 1             # config 1: 512 CTAs already
+    assert ggs.choose_split(8, 500, 256, 256) == 1              # config 2, 8 neighbours: likewise
+    assert ggs.choose_split(1, 4000, 512, 512) == 1             # deep genome: keep the saturation stop
+    for B, N, side in ((32, 100, 128), (8, 500, 256), (4, 20, 64), (3, 1000, 512), (2, 500, 256)):
         tiles = ((side + 31) // 32) ** 2
         k = ggs.choose_split(B, N, side, side)
         assert k in (1, 2, 4, 8) and B * tiles * k <= max(slots, B * tiles)
@@ -127,7 +130,7 @@ def test_automatic_split_policy(ggs):
 
 def test_host_path_and_render_entries_on_the_small_batch_path(ggs):
     from ggs_b200 import synth
-    B, N, H, W = 6, 200, 128, 128
+    B, N, H, W = 3, 200, 128, 128
     g = synth.new_population_np(B, N, H, W, seed=12)
     t = synth.synthetic_target_np(H, W, 12)
     assert ggs.choose_split(B, N, H, W) > 1

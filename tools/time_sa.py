@@ -25,12 +25,12 @@ for batched in (False, True):
   for loop in ("0", "1"):
       os.environ["GGS_B200_SA_LOOP"] = loop
       res = []
-      for iters in (0, ITERS):
+      for iters in (0, ITERS, ITERS):   # the first long run pays one-time costs (allocator, lazy module loading)
           torch.manual_seed(1); random.seed(1)
           torch.cuda.synchronize(); t0 = time.perf_counter()
           _, e = simulated_annealing(target, iterations=iters, **kw)
           torch.cuda.synchronize(); res.append((time.perf_counter() - t0, e))
-      dt = res[1][0] - res[0][0]
+      dt = res[2][0] - res[0][0]
       print(f"{'python loop' if loop == '1' else 'device engine'}: {H}x{W}, {N} splats, {TRIES} tries/iteration: "
             f"{ITERS} iterations in {dt:.3f} s beyond the {res[0][0]:.3f} s set-up = {ITERS / dt:.0f} iterations/s "
-            f"({ITERS * TRIES / dt:.0f} tries/s); energy {res[0][1]:.6f} -> {res[1][1]:.6f}")
+            f"({ITERS * TRIES / dt:.0f} tries/s); energy {res[0][1]:.6f} -> {res[2][1]:.6f}")
