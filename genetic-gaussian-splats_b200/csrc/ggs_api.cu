@@ -224,7 +224,8 @@ int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, 
     q.split = stats ? 1 : (opt.split != 0 ? opt.split : choose_split(B, N, H, W));
     const int fuse = stats ? 0 : (opt.fuse >= 0 ? opt.fuse : options().fuse);
     const int64_t ctas = (int64_t)B * tiles_x(W) * tiles_y(H) * q.split;
-    q.fused = N > 0 && fuse != 0 && fused_decode_possible(N, q.split) && (fuse == 1 || ctas <= wave_slots());
+    q.small_grid = ctas <= wave_slots();
+    q.fused = N > 0 && fuse != 0 && fused_decode_possible(N, q.split) && (fuse == 1 || q.small_grid);
 
     cudaEvent_t *ev = timing_slot();
     if (ev) GGS_CUDA(cudaEventRecord(ev[0], stream));

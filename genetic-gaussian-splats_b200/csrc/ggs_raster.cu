@@ -40,15 +40,16 @@
 //
 // Two kernels share the list building, the composite and the epilogue below:
 //   raster_kernel        one CTA per (candidate, tile): the throughput path (populations);
-//   raster_split_kernel  the latency path for small batches (SA neighbours, a 32-individual GA,
-//                        single frames), where one CTA per tile leaves most of the GPU idle: a
+//   raster_split_kernel  the latency path for very small batches (one SA try, a single frame, a
+//                        handful of candidates), where one CTA per tile leaves most SMs idle: a
 //                        thread-block CLUSTER of K = 2 / 4 / 8 CTAs shares a tile, CTA k composites
 //                        the k-th segment of the genome front to back on its own, and the K partial
 //                        (colour, transmittance) states -- "over" is associative:
 //                        (C1,T1) o (C2,T2) = (C1 + T1 C2, T1 T2) -- are folded in genome order
 //                        through distributed shared memory, each CTA finishing 1/K of the tile's
 //                        pixels.  Its fused variant also decodes the genome rows itself (the
-//                        arithmetic of ggs_decode_math.cuh), so an evaluation is ONE launch.
+//                        arithmetic of ggs_decode_math.cuh): ONE launch per evaluation, but
+//                        measured slower than decode + raster and therefore off by default.
 // This file is compiled with -fmad=false (ggs_decode_math.cuh): every FMA below is explicit.
 #include <cooperative_groups.h>
 
@@ -72,6 +73,12 @@ static_assert(GGS_SCAN_CHUNK <= kListCap, "a scan round must fit the list");
 constexpr int kScanChunk = kThreads * kScanPerThread;
 #ifndef GGS_OPT_NOFINALSYNC
 #define GGS_OPT_NOFINALSYNC 1   // neutral at config 3, 4 % of a small launch
+#endif
+#ifndef GGS_OPT_EARLY_LOADS
+#define GGS_OPT_EARLY_LOADS 0
+#endif
+#ifndef GGS_OPT_PREFETCH
+#define GGS_OPT_PREFETCH 1
 #endif
 #ifndef GGS_EPI_BATCH
 #define GGS_EPI_BATCH 4   // rows whose fitness inputs are loaded together in the epilogue (8 spills the pixel state)
@@ -300,10 +307,24 @@ __device__ __forceinline__ bool composite_list(PixelState &px, const float4 *__r
 #undef GGS_TMAX
             if (__all_sync(0xffffffffu, tmax < kOpaque)) return false;
         }
+#if GGS_OPT_EARLY_LOADS
+        // issued with q2 so that their latency hides behind the band test; volatile asm, or the
+        // compiler sinks the loads back below the branch
+        float4 q0, q1;
+        {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(q);
+            asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(q0.x), "=f"(q0.y), "=f"(q0.z), "=f"(q0.w) : "r"(sa));
+            asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];"
+                         : "=f"(q1.x), "=f"(q1.y), "=f"(q1.z), "=f"(q1.w) : "r"(sa));
+        }
+#endif
         const unsigned c = __byte_perm(__float_as_uint(q2.z), 0u, band_sel);  // this band's byte
         if (c == kBandMiss) continue;  // warp-uniform
+#if !GGS_OPT_EARLY_LOADS
         const float4 q0 = q[0];
         const float4 q1 = q[1];
+#endif
         const bool in_x = (__float_as_uint(q2.y) & lanebit) != 0u;
         const float qx = Xf - q0.x;
         const float t1 = q0.w * qx;                       // Bq*qx
@@ -380,6 +401,7 @@ struct RasterArgs {
     float *fitness;   // [B]
     unsigned long long *stats;
     int split;  // CTAs per (candidate, tile): the cluster size of raster_split_kernel
+    int prefetch_inputs;  // latency regime: pull the tile's target / mask lines into L1 up front
     PeerStores peers;  // fitness stores into the other GPUs' gathered vectors (ggs_peers.cu)
 };
 
@@ -683,7 +705,12 @@ __device__ __noinline__ void reduce_and_finish(const RasterArgs &a, int b, int p
 // (3 lines of target + 1 of mask) -- BEFORE the grid dependency wait; by the epilogue it sits in L1.
 __device__ __forceinline__ void prefetch_tile_inputs(const RasterArgs &a, const TileGeom &g, int tid)
 {
-    if (a.target == nullptr || g.X0 >= a.W) return;
+#if !GGS_OPT_PREFETCH
+    return;
+#endif
+    // only for grids of at most one wave: at config 3 the extra L2 -> L1 fills (16 KB per CTA next
+    // to ~19 KB of boxes and records) cost 0.45 % and the epilogue's latency is hidden anyway
+    if (!a.prefetch_inputs || a.target == nullptr || g.X0 >= a.W) return;
     const int px = min(kTileW, a.W - g.X0);  // pixels of a row inside the image
     const int part = tid & 3;
     for (int r = tid >> 2; r < kTileH; r += kThreads / 4) {
@@ -885,6 +912,7 @@ cudaError_t launch_raster(const RasterLaunch &q, cudaStream_t stream)
     a.fitness = q.d_fitness;
     a.stats = q.d_stats;
     a.split = split;
+    a.prefetch_inputs = q.small_grid ? 1 : 0;
     a.peers = q.peers;
     if (q.fused) {
         if (!fused_decode_possible(q.N, split)) return cudaErrorInvalidConfiguration;

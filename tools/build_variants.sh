@@ -16,7 +16,7 @@ while [ $# -gt 1 ]; do
   nvcc $COMMON -fmad=false -c $PKG/csrc/ggs_mask.cu -o $B/mask.o &
   nvcc $COMMON -c $PKG/csrc/ggs_engine.cu -o $B/engine.o &
   nvcc $COMMON -c $PKG/csrc/ggs_peers.cu -o $B/peers.o &
-  nvcc $COMMON $flags -fmad=false -Xptxas -v -c $PKG/csrc/ggs_raster.cu -o $B/raster.o 2>&1 | grep -E "Used|spill" | grep -A1 -B0 "spill" | head -4 | sed "s/^/$name: /"
+  nvcc $COMMON $flags ${RASTER_FMAD--fmad=false} -Xptxas -v -c $PKG/csrc/ggs_raster.cu -o $B/raster.o 2>&1 | grep -E "Used|spill" | grep -A1 -B0 "spill" | head -4 | sed "s/^/$name: /"
   wait
   nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT/libggs_$name.so $B/decode.o $B/raster.o $B/probe.o $B/api.o $B/breed.o $B/mask.o $B/engine.o $B/peers.o
 done
