@@ -138,6 +138,7 @@ __device__ __forceinline__ f2_t add2(f2_t a, f2_t b)
     return d;
 }
 
+#if defined(GGS_NAMED_REGS) && !GGS_NAMED_REGS   // only the C++ fallback of the pixel state uses these
 __device__ __forceinline__ f2_t mul2(f2_t a, f2_t b)
 {
     f2_t d;
@@ -150,6 +151,7 @@ __device__ __forceinline__ f2_t sub2(f2_t a, f2_t b)
     asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+#endif
 
 // ---- pixel state ----------------------------------------------------------------------------
 // Pair k of a thread holds rows (2k, 2k+1) of its column: accumulated colour (premultiplied,
