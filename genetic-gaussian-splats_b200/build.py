@@ -29,7 +29,7 @@ SOURCES = {
     # the packed (64-bit) pixel accumulators live in named PTX registers (GGS_NAMED_REGS), which
     # keeps ptxas from renaming them out of place at any -O level; tests/test_cpu_sass.py guards it
     "ggs_raster.cu": ["-fmad=false"],   # it inlines the decode arithmetic (fused path)
-    "ggs_breed.cu": [],
+    "ggs_breed.cu": ["-fmad=false"],    # its SA proposal kernel inlines the decode arithmetic
     "ggs_mask.cu": ["-fmad=false"],   # one rounding per operation, like the reference's torch ops
     "ggs_engine.cu": [],
     "ggs_peers.cu": [],

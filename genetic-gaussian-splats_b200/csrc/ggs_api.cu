@@ -225,14 +225,15 @@ int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, 
     const int fuse = stats ? 0 : (opt.fuse >= 0 ? opt.fuse : options().fuse);
     const int64_t ctas = (int64_t)B * tiles_x(W) * tiles_y(H) * q.split;
     q.small_grid = ctas <= wave_slots();
-    q.fused = N > 0 && fuse != 0 && fused_decode_possible(N, q.split) && (fuse == 1 || q.small_grid);
+    q.fused = !opt.decoded && N > 0 && fuse != 0 && fused_decode_possible(N, q.split) &&
+              (fuse == 1 || q.small_grid);
 
     cudaEvent_t *ev = timing_slot();
     if (ev) GGS_CUDA(cudaEventRecord(ev[0], stream));
     if (q.fused) {
         // no decode launch clears the ticket counters: do it here unless their owner vouches for them
         if (!opt.counters_zeroed) GGS_CUDA(cudaMemsetAsync(q.ws.counter, 0, (size_t)B * sizeof(int), stream));
-    } else {
+    } else if (!opt.decoded) {
         GGS_CUDA(launch_decode(d_genomes, layout, (int64_t)B * N, cols, H, W, k_sigma, q.ws.rec, q.ws.aabb,
                                nullptr, nullptr, q.ws.counter, B, stream));
     }

@@ -28,14 +28,23 @@
 // splat, stream), so a step is reproducible for a given (seed, generation) and independent of
 // the launch geometry.  The operators draw from the same distributions as the reference; the
 // random streams necessarily differ (GA trajectory parity is not a goal).
+//
+// propose_kernel (below) is the same operator specialised for simulated annealing: children
+// of ONE parent, no crossover, one CTA per child with the whole child in shared memory, and the
+// decode of the finished rows (ggs_decode_math.cuh) in the same launch -- a sequential SA try is
+// then propose -> raster -> Metropolis instead of breed -> decode -> raster -> Metropolis.  It
+// uses the same counters and the same helpers, so it produces the same bits as breed_kernel.
+// This file is compiled with -fmad=false because of the decode arithmetic.
 #include <math.h>
 
-#include "ggs_common.cuh"
+#include "ggs_decode_math.cuh"
 
 namespace ggs {
 namespace {
 
 constexpr int kBreedThreads = 256;
+constexpr int kProposeThreads = 512;
+constexpr int kProposeMaxSplats = 4096;  // the child lives in shared memory: 36 B + 1 B per splat
 constexpr int kGroups = 5;  // xy, log-scales, theta, rgb, alpha
 constexpr size_t kStageBytes = (size_t)2 * 2 * kBreedThreads * 9 * sizeof(float);
 
@@ -490,7 +499,193 @@ __global__ void __launch_bounds__(kBreedThreads) breed_kernel(BreedParams q)
     }
 }
 
+// ---- simulated annealing: mutated copies of one parent, decoded in the same launch -----------
+struct ProposeParams {
+    BreedParams q;   // pop = the parent [N][cols] (P = 1), off = the children [n_children][N][9]
+    float4 *rec;     // decoded records of the children: the workspace of their evaluation
+    uint2 *aabb;
+    int *counters;   // [n_children] raster tickets, cleared here (the decode launch would)
+    int H, W;
+    float k_sigma;
+};
+
+__global__ void __launch_bounds__(kProposeThreads) propose_kernel(const __grid_constant__ ProposeParams p)
+{
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    const BreedParams &q = p.q;
+    float *s_rows = reinterpret_cast<float *>(s_dyn);                 // [N][9]
+    unsigned char *s_mask = s_dyn + (size_t)q.N * 9 * sizeof(float);  // [N]
+    __shared__ int s_count[4], s_force[4];
+    __shared__ unsigned long long s_best;
+    __shared__ int s_swap_i;
+    __shared__ unsigned s_swap_salt;
+    __shared__ float s_size_i;
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned child = blockIdx.x;
+    pdl_wait();
+    pdl_trigger();
+    if (tid < 4) {
+        s_count[tid] = 0;
+        s_force[tid] = -1;
+    }
+    if (tid == 0) {
+        s_best = 0ull;
+        const U4 r = philox4x32_10(q.gen, child, 0, kSwapIdx, q.seed_lo, q.seed_hi);
+        s_swap_i = (q.N >= 2) ? (int)__umulhi(r.x, (unsigned)(q.N - 1)) : 0;
+        s_swap_salt = r.y;
+        p.counters[child] = 0;
+    }
+    __syncthreads();
+
+    // pass 1: the masks, and how many genes of each group mutate ("at least one" rule)
+    int cnt[4] = {0, 0, 0, 0};
+    for (int n = tid; n < q.N; n += kProposeThreads) {
+        const unsigned m = gene_masks(q, child, n);
+        s_mask[n] = (unsigned char)m;
+        cnt[0] += __popc(m & 3u);
+        cnt[1] += __popc(m & 12u);
+        cnt[2] += __popc(m & 16u);
+        cnt[3] += __popc(m & 96u);
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        int v = cnt[g];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v) atomicAdd(&s_count[g], v);
+    }
+    __syncthreads();
+    if (tid < 4 && s_count[tid] == 0) {  // an empty group gets one uniformly chosen element forced on
+        const int width = (tid == 2) ? 1 : 2;
+        const U4 r = philox4x32_10(q.gen, child, tid, kForce, q.seed_lo, q.seed_hi);
+        s_force[tid] = (int)__umulhi(r.x, (unsigned)(q.N * width));
+    }
+    __syncthreads();
+
+    // pass 2: mutation and projection of every row, into shared memory
+    const int f0 = s_force[0], f1 = s_force[1], f2 = s_force[2], f3 = s_force[3];
+    const int swap_i = s_swap_i;
+    for (int n = tid; n < q.N; n += kProposeThreads) {
+        const float *src = q.pop + (int64_t)n * q.cols;
+        float g[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g[k] = __ldg(src + k);
+        unsigned m = s_mask[n] & kFlagBits;
+        if (f0 >= 0 && (f0 >> 1) == n) m |= 1u << (f0 & 1);
+        if (f1 >= 0 && (f1 >> 1) == n) m |= 4u << (f1 & 1);
+        if (f2 >= 0 && f2 == n) m |= 16u;
+        if (f3 >= 0 && (f3 >> 1) == n) m |= 32u << (f3 & 1);
+        const unsigned gmask = group_bits(m);
+#pragma unroll
+        for (int grp = 0; grp < kGroups; ++grp)
+            if (gmask & (1u << grp)) mutate_group(q, child, n, grp, m, g);
+        project_row(q, g);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s_rows[n * 9 + k] = g[k];
+        if (n == swap_i) s_size_i = g[2] + g[3];  // log(sigma_x * sigma_y)
+    }
+    __syncthreads();
+
+    // bring a bigger later splat forward (genetic.py:74-91)
+    if (q.N >= 2) {
+        unsigned long long best = 0ull;
+        const float size_i = s_size_i;
+        const unsigned salt = s_swap_salt;
+        for (int j = swap_i + 1 + tid; j < q.N; j += kProposeThreads) {
+            if (s_rows[j * 9 + 2] + s_rows[j * 9 + 3] > size_i) {
+                const unsigned long long key = swap_key(salt, j);
+                best = key > best ? key : best;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if (lane == 0 && best) atomicMax(&s_best, best);
+        __syncthreads();
+        if (tid < 9 && s_best != 0ull) {
+            const int j = (int)(s_best & 0xffffffffull);
+            const float a = s_rows[swap_i * 9 + tid], b = s_rows[j * 9 + tid];
+            s_rows[swap_i * 9 + tid] = b;
+            s_rows[j * 9 + tid] = a;
+        }
+        __syncthreads();
+    }
+
+    // the child: genome rows for the caller, decoded records for the raster
+    float *dst = q.off + (int64_t)child * q.N * 9;
+    for (int i = tid; i < q.N * 9; i += kProposeThreads) dst[i] = s_rows[i];
+    for (int n = tid; n < q.N; n += kProposeThreads) {
+        float g[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) g[k] = s_rows[n * 9 + k];
+        const Decoded d = decode_chol(encode_axes(g), p.H, p.W, p.k_sigma);
+        SplatRec r;
+        uint2 box;
+        make_record(d, r, box);
+        const int64_t row = (int64_t)child * q.N + n;
+        const float4 *rv = reinterpret_cast<const float4 *>(&r);
+        p.rec[row * 3 + 0] = rv[0];
+        p.rec[row * 3 + 1] = rv[1];
+        p.rec[row * 3 + 2] = rv[2];
+        p.aabb[row] = box;
+    }
+}
+
 }  // namespace
+
+bool propose_possible(int N, int cols) { return N >= 1 && N <= kProposeMaxSplats && cols >= 9; }
+
+cudaError_t launch_propose(const float *d_parent, int N, int cols, int n_children, float *d_children,
+                           float mutpb, const float sigma6[6], float log_lo, float log_hi,
+                           uint64_t seed, uint32_t generation, const Workspace &ws, int H, int W,
+                           float k_sigma, cudaStream_t stream)
+{
+    if (n_children <= 0) return cudaSuccess;
+    ProposeParams p;
+    BreedParams &q = p.q;
+    q.pop = d_parent;
+    q.fitness = nullptr;
+    q.off = d_children;
+    q.P = 1;
+    q.N = N;
+    q.cols = cols;
+    q.n_children = n_children;
+    q.tour_k = 1;
+    q.cxpb = 0.0f;
+    const float thr = rintf(fminf(fmaxf(mutpb, 0.0f), 1.0f) * 65536.0f);
+    q.mut_thr = (unsigned)thr;
+    q.s_xy = sigma6[0];
+    q.s_alog = sigma6[1];
+    q.s_blog = sigma6[2];
+    q.s_theta = sigma6[3];
+    q.s_rgb = sigma6[4];
+    q.s_alpha = sigma6[5];
+    q.log_lo = log_lo;
+    q.log_hi = log_hi;
+    q.seed_lo = (unsigned)(seed & 0xffffffffu);
+    q.seed_hi = (unsigned)(seed >> 32);
+    q.gen = generation;
+    p.rec = ws.rec;
+    p.aabb = ws.aabb;
+    p.counters = ws.counter;
+    p.H = H;
+    p.W = W;
+    p.k_sigma = k_sigma;
+    const size_t smem = (size_t)N * 9 * sizeof(float) + (size_t)N;
+    static size_t granted[64] = {};
+    int dev = 0;
+    if (smem > (size_t)40 * 1024 && cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64 &&
+        granted[dev] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(propose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+        granted[dev] = smem;
+    }
+    return launch_kernel(propose_kernel, n_children, kProposeThreads, smem, stream, p);
+}
 
 cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int N, int cols,
                          int n_children, float *d_offspring, int tour_k, float cxpb, float mutpb,

@@ -120,6 +120,15 @@ cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int 
                          const float sigma6[6], float log_lo, float log_hi, uint64_t seed,
                          uint32_t generation, cudaStream_t stream);
 
+// Simulated annealing's proposal step: n_children mutated copies of one parent (no selection, no
+// crossover: the same bits launch_breed gives for a one-individual population) AND their decoded
+// records, written into the workspace of the evaluation that follows (EvalOptions::decoded).
+bool propose_possible(int N, int cols);
+cudaError_t launch_propose(const float *d_parent, int N, int cols, int n_children, float *d_children,
+                           float mutpb, const float sigma6[6], float log_lo, float log_hi,
+                           uint64_t seed, uint32_t generation, const Workspace &ws, int H, int W,
+                           float k_sigma, cudaStream_t stream);
+
 size_t mask_workspace_bytes(int H, int W);
 cudaError_t launch_importance_mask(const float *d_image, int H0, int W0, int H, int W, int div255,
                                    const int *scales, int n_scales, float w_edge, float w_var,
@@ -280,6 +289,8 @@ struct EvalOptions {
     int fuse = -1;   // decode inside the raster: -1 = when it pays (one wave) and fits, 0 = never, 1 = if it fits
     bool counters_zeroed = false;  // the workspace's ticket counters are known to be zero (its owner
                                    // cleared them once; every launch leaves them zero)
+    bool decoded = false;  // records, cull boxes and cleared counters of these B x N splats are in the
+                           // workspace already (launch_propose): skip the decode launch
     PeerStores peers;
 };
 int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, int W,

@@ -700,12 +700,32 @@ int ggs_sa_set_target(ggs_sa *g, const float *d_target, const float *d_mask, int
     return GGS_OK;
 }
 
-static int sa_energy(ggs_sa *g, const float *genomes, int B, cudaStream_t st)
+static int sa_energy(ggs_sa *g, const float *genomes, int B, cudaStream_t st, bool decoded = false)
 {
     const float bg[3] = {1.0f, 1.0f, 1.0f};
+    EvalOptions opt = owned_workspace();
+    opt.decoded = decoded;  // the proposal kernel has written the records of these B candidates
     return evaluate(genomes, GGS_LAYOUT_AXES_ANGLE, B, g->N, 9, g->H, g->W, g->k_sigma, bg, g->target,
                     g->mode == GGS_MODE_PLAIN ? nullptr : g->mask, g->mode, g->beta, g->energy,
-                    nullptr, 0, g->ws, g->ws_bytes, st, owned_workspace());
+                    nullptr, 0, g->ws, g->ws_bytes, st, opt);
+}
+
+// `count` mutated copies of the current state into g->cand, proposal stream `number`.  When the
+// state fits the proposal kernel (ggs_breed.cu) the children come out decoded as well and the
+// evaluation that follows skips its decode launch; otherwise the general breeding kernel runs.
+static int sa_propose(ggs_sa *g, int count, const float *sigma6, float mutpb, float log_lo, float log_hi,
+                      uint32_t number, cudaStream_t st, bool *decoded)
+{
+    *decoded = propose_possible(g->N, 9);
+    if (*decoded) {
+        GGS_TRY(launch_propose(g->current, g->N, 9, count, g->cand, mutpb, sigma6, log_lo, log_hi, g->seed,
+                               number, carve_workspace(g->ws, count, g->N, g->H, g->W), g->H, g->W,
+                               g->k_sigma, st));
+    } else {
+        GGS_TRY(launch_breed(g->current, g->dummy_fit, 1, g->N, 9, count, g->cand, 1, 0.0f, mutpb, sigma6,
+                             log_lo, log_hi, g->seed, number, st));
+    }
+    return GGS_OK;
 }
 
 int ggs_sa_start(ggs_sa *g, const float *d_state, int cols, uint64_t seed, void *stream)
@@ -785,10 +805,11 @@ int ggs_sa_run(ggs_sa *g, int count, const float *h_sigma6, const double *h_temp
             // accepted or rejected before the next one is proposed.  Proposal number
             // (it - 1) * tries + t + 1 keys the random stream, as in the Python-driven loop.
             for (int t = 0; t < g->tries; ++t) {
-                GGS_TRY(launch_breed(g->current, g->dummy_fit, 1, g->N, 9, 1, g->cand, 1, 0.0f, mutpb,
-                                     h_sigma6 + 6 * (size_t)k, log_scale_lo, log_scale_hi, g->seed,
-                                     (uint32_t)((size_t)(it - 1) * g->tries + t + 1), st));
-                int rc = sa_energy(g, g->cand, 1, st);
+                bool decoded = false;
+                int rc = sa_propose(g, 1, h_sigma6 + 6 * (size_t)k, mutpb, log_scale_lo, log_scale_hi,
+                                    (uint32_t)((size_t)(it - 1) * g->tries + t + 1), st, &decoded);
+                if (rc) return rc;
+                rc = sa_energy(g, g->cand, 1, st, decoded);
                 if (rc) return rc;
                 q.uniform[0] = h_uniform[(size_t)k * g->tries + t];
                 q.tries = 1;
@@ -798,10 +819,11 @@ int ggs_sa_run(ggs_sa *g, int count, const float *h_sigma6, const double *h_temp
             // `tries` independently mutated copies of the current state: the breeding kernel with a
             // one-individual population and no crossover (annealing.py:121-128, batched), one
             // evaluation of all of them, the Metropolis tests applied in order
-            GGS_TRY(launch_breed(g->current, g->dummy_fit, 1, g->N, 9, g->tries, g->cand, 1, 0.0f, mutpb,
-                                 h_sigma6 + 6 * (size_t)k, log_scale_lo, log_scale_hi, g->seed,
-                                 (uint32_t)it, st));
-            int rc = sa_energy(g, g->cand, g->tries, st);
+            bool decoded = false;
+            int rc = sa_propose(g, g->tries, h_sigma6 + 6 * (size_t)k, mutpb, log_scale_lo, log_scale_hi,
+                                (uint32_t)it, st, &decoded);
+            if (rc) return rc;
+            rc = sa_energy(g, g->cand, g->tries, st, decoded);
             if (rc) return rc;
             for (int t = 0; t < g->tries; ++t) q.uniform[t] = h_uniform[(size_t)k * g->tries + t];
             q.tries = g->tries;

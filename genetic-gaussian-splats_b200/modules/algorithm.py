@@ -222,6 +222,8 @@ def genetic_approx(target_img_uint8: torch.Tensor,
                 peers=peers)   # ranks may cut their blocks differently: epochs count generations
             if peers is not None:
                 peers.check()
+                import torch.distributed as dist
+                dist.barrier()     # nobody unmaps a buffer another rank may still be writing to
                 peers.close()
         else:
             best_ind, best_fit, curves = _generations_in_python(

@@ -12,7 +12,7 @@ while [ $# -gt 1 ]; do
   nvcc $COMMON $flags -fmad=false -c $PKG/csrc/ggs_decode.cu -o $B/decode.o &
   nvcc $COMMON $flags -c $PKG/csrc/ggs_probe.cu -o $B/probe.o &
   nvcc $COMMON $flags -c $PKG/csrc/ggs_api.cu -o $B/api.o &
-  nvcc $COMMON $flags -c $PKG/csrc/ggs_breed.cu -o $B/breed.o &
+  nvcc $COMMON $flags -fmad=false -c $PKG/csrc/ggs_breed.cu -o $B/breed.o &
   nvcc $COMMON -fmad=false -c $PKG/csrc/ggs_mask.cu -o $B/mask.o &
   nvcc $COMMON -c $PKG/csrc/ggs_engine.cu -o $B/engine.o &
   nvcc $COMMON -c $PKG/csrc/ggs_peers.cu -o $B/peers.o &
