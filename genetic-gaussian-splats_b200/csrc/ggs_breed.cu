@@ -507,6 +507,7 @@ struct ProposeParams {
     int *counters;   // [n_children] raster tickets, cleared here (the decode launch would)
     int H, W;
     float k_sigma;
+    ProposeJudge judge;  // the Metropolis step of the evaluation that preceded this proposal
 };
 
 __global__ void __launch_bounds__(kProposeThreads) propose_kernel(const __grid_constant__ ProposeParams p)
@@ -521,10 +522,58 @@ __global__ void __launch_bounds__(kProposeThreads) propose_kernel(const __grid_c
     __shared__ unsigned s_swap_salt;
     __shared__ float s_size_i;
 
+    __shared__ int s_judged_cur, s_judged_best;
+
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned child = blockIdx.x;
     pdl_wait();
     pdl_trigger();
+
+    // ---- judge the previous candidates (annealing.py:129-146); every CTA reaches the same verdict
+    const ProposeJudge &J = p.judge;
+    if (tid == 0) {
+        int cur = -1, best = -1;
+        if (J.tries > 0) {
+            double e_cur = J.e_in[0], e_best = J.e_in[1];
+            for (int k = 0; k < J.tries; ++k) {
+                const double e_new = (double)J.energy[k];
+                const double dE = e_new - e_cur;
+                if (dE <= 0.0 || (J.temperature > 0.0 && J.uniform[k] < exp(-dE / J.temperature))) {
+                    cur = k;
+                    e_cur = e_new;
+                }
+                if (e_cur + 1e-12 < e_best) {
+                    e_best = e_cur;
+                    best = cur;
+                }
+            }
+            if (blockIdx.x == 0) {
+                J.e_out[0] = e_cur;
+                J.e_out[1] = e_best;
+                J.curve[0] = e_best;
+                J.curve[1] = e_cur;
+            }
+        }
+        s_judged_cur = cur;
+        s_judged_best = best;
+    }
+    __syncthreads();
+    const int64_t row_floats = (int64_t)q.N * 9;
+    const float *parent = q.pop;  // the current state ...
+    int parent_cols = q.cols;
+    if (s_judged_cur >= 0) {      // ... unless a candidate of the previous batch was accepted
+        parent = J.cand_prev + s_judged_cur * row_floats;
+        parent_cols = 9;
+    }
+    if (blockIdx.x == 0 && J.tries > 0) {  // nobody reads `current` when it is being replaced
+        if (s_judged_best >= 0)
+            for (int64_t i = tid; i < row_floats; i += kProposeThreads)
+                J.best[i] = J.cand_prev[s_judged_best * row_floats + i];
+        if (s_judged_cur >= 0)
+            for (int64_t i = tid; i < row_floats; i += kProposeThreads) J.current[i] = parent[i];
+    }
+    if (q.n_children == 0) return;  // a judging-only launch
+
     if (tid < 4) {
         s_count[tid] = 0;
         s_force[tid] = -1;
@@ -567,10 +616,10 @@ __global__ void __launch_bounds__(kProposeThreads) propose_kernel(const __grid_c
     const int f0 = s_force[0], f1 = s_force[1], f2 = s_force[2], f3 = s_force[3];
     const int swap_i = s_swap_i;
     for (int n = tid; n < q.N; n += kProposeThreads) {
-        const float *src = q.pop + (int64_t)n * q.cols;
+        const float *src = parent + (int64_t)n * parent_cols;
         float g[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) g[k] = __ldg(src + k);
+        for (int k = 0; k < 9; ++k) g[k] = src[k];
         unsigned m = s_mask[n] & kFlagBits;
         if (f0 >= 0 && (f0 >> 1) == n) m |= 1u << (f0 & 1);
         if (f1 >= 0 && (f1 >> 1) == n) m |= 4u << (f1 & 1);
@@ -641,9 +690,10 @@ bool propose_possible(int N, int cols) { return N >= 1 && N <= kProposeMaxSplats
 cudaError_t launch_propose(const float *d_parent, int N, int cols, int n_children, float *d_children,
                            float mutpb, const float sigma6[6], float log_lo, float log_hi,
                            uint64_t seed, uint32_t generation, const Workspace &ws, int H, int W,
-                           float k_sigma, cudaStream_t stream)
+                           float k_sigma, const ProposeJudge &judge, cudaStream_t stream)
 {
-    if (n_children <= 0) return cudaSuccess;
+    if (n_children <= 0 && judge.tries <= 0) return cudaSuccess;
+    if (n_children < 0) n_children = 0;
     ProposeParams p;
     BreedParams &q = p.q;
     q.pop = d_parent;
@@ -674,6 +724,7 @@ cudaError_t launch_propose(const float *d_parent, int N, int cols, int n_childre
     p.H = H;
     p.W = W;
     p.k_sigma = k_sigma;
+    p.judge = judge;
     const size_t smem = (size_t)N * 9 * sizeof(float) + (size_t)N;
     static size_t granted[64] = {};
     int dev = 0;
@@ -684,7 +735,7 @@ cudaError_t launch_propose(const float *d_parent, int N, int cols, int n_childre
         if (e != cudaSuccess) return e;
         granted[dev] = smem;
     }
-    return launch_kernel(propose_kernel, n_children, kProposeThreads, smem, stream, p);
+    return launch_kernel(propose_kernel, n_children > 0 ? n_children : 1, kProposeThreads, smem, stream, p);
 }
 
 cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int N, int cols,

@@ -123,11 +123,32 @@ cudaError_t launch_breed(const float *d_pop, const float *d_fitness, int P, int 
 // Simulated annealing's proposal step: n_children mutated copies of one parent (no selection, no
 // crossover: the same bits launch_breed gives for a one-individual population) AND their decoded
 // records, written into the workspace of the evaluation that follows (EvalOptions::decoded).
+//
+// The kernel also JUDGES the evaluation that preceded it (annealing.py:129-146), so that a try is
+// two launches -- propose, raster -- and not four: with judge.tries > 0 every CTA replays the
+// Metropolis tests on the `tries` energies of the previous candidates (accept when dE <= 0 or
+// u < exp(-dE / T); the best-so-far test follows every try) and mutates the state they leave --
+// an accepted candidate of the previous batch, or the current state -- while CTA 0 records the
+// outcome: energies (read from e_in, written to e_out: the other CTAs still read e_in), the curve
+// point, the current / best rows.  n_children = 0 only judges (the trailing launch of a block).
+constexpr int kMaxTries = 64;
+struct ProposeJudge {
+    int tries = 0;                    // 0: nothing to judge
+    const float *energy = nullptr;    // [tries] fitness of the previous candidates
+    const float *cand_prev = nullptr; // [tries][N][9] the previous candidates
+    float *current = nullptr;         // [N][9] in / out
+    float *best = nullptr;            // [N][9] in / out
+    const double *e_in = nullptr;     // {e_current, e_best} before
+    double *e_out = nullptr;          // {e_current, e_best} after
+    double *curve = nullptr;          // (best, current) of the judged iteration
+    double temperature = 0.0;
+    double uniform[kMaxTries] = {};   // one U[0,1) draw per try (used when the try is uphill)
+};
 bool propose_possible(int N, int cols);
 cudaError_t launch_propose(const float *d_parent, int N, int cols, int n_children, float *d_children,
                            float mutpb, const float sigma6[6], float log_lo, float log_hi,
                            uint64_t seed, uint32_t generation, const Workspace &ws, int H, int W,
-                           float k_sigma, cudaStream_t stream);
+                           float k_sigma, const ProposeJudge &judge, cudaStream_t stream);
 
 size_t mask_workspace_bytes(int H, int W);
 cudaError_t launch_importance_mask(const float *d_image, int H0, int W0, int H, int W, int div255,

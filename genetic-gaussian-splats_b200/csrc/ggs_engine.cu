@@ -171,8 +171,6 @@ __global__ void __launch_bounds__(kSelectThreads) select_kernel(SelectParams q)
 }
 
 // ---- simulated annealing: the Metropolis step of one iteration (annealing.py:125-137) ----------
-constexpr int kMaxTries = 64;
-
 struct MetropolisParams {
     const float *cand;     // [tries][N][9] neighbours, all proposed from the current state
     const float *energy;   // [tries]
@@ -589,7 +587,10 @@ struct ggs_sa {
     int device = 0;
     int N = 0, H = 0, W = 0, tries = 0, capacity = 0;
     float *current = nullptr, *best = nullptr;  // [N][9]
-    float *cand = nullptr;                       // [tries][N][9]
+    float *cand2[2] = {nullptr, nullptr};        // [tries][N][9] each: proposals alternate, so that a
+                                                 // proposal can read an accepted candidate of the
+                                                 // previous batch while it writes the next one
+    int cw = 0;                                  // the buffer holding the latest proposals
     float *energy = nullptr;                     // [tries]
     float *dummy_fit = nullptr;                  // [1] fitness of the single "parent"
     float *target = nullptr, *mask = nullptr;
@@ -598,11 +599,21 @@ struct ggs_sa {
     void *ws = nullptr;
     size_t ws_bytes = 0;
     double *curves = nullptr;  // [capacity][2]
-    double *e_current = nullptr, *e_best = nullptr;
+    double *e_state = nullptr;  // [2][2]: {e_current, e_best}, two copies used alternately (a judging
+                                // launch reads one and writes the other)
+    int ep = 0;                 // the copy that holds the settled values
     uint64_t seed = 0;
     int iteration = -1;
     bool has_target = false;
     bool sequential = true;  // the reference's chain (annealing.py:121-146); false: batched neighbours
+    // the evaluation still waiting for its Metropolis step: the next proposal launch judges it
+    struct Pending {
+        bool on = false;
+        int tries = 0, cand = 0;
+        double temperature = 0.0;
+        double uniform[kMaxTries] = {};
+        double *curve = nullptr;
+    } pending;
 };
 
 extern "C" {
@@ -643,7 +654,7 @@ int ggs_sa_create(int device, int N, int H, int W, int tries, int max_iterations
     g->ws_bytes = workspace_bytes(tries, N, H, W);
     cudaError_t e = cudaMalloc(&g->current, row);
     if (e == cudaSuccess) e = cudaMalloc(&g->best, row);
-    if (e == cudaSuccess) e = cudaMalloc(&g->cand, row * tries);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaMalloc(&g->cand2[i], row * tries);
     if (e == cudaSuccess) e = cudaMalloc(&g->energy, (size_t)tries * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&g->dummy_fit, sizeof(float));
     if (e == cudaSuccess) e = cudaMemset(g->dummy_fit, 0, sizeof(float));
@@ -652,8 +663,7 @@ int ggs_sa_create(int device, int N, int H, int W, int tries, int max_iterations
     if (e == cudaSuccess) e = cudaMalloc(&g->ws, g->ws_bytes);
     if (e == cudaSuccess) e = cudaMemset(g->ws, 0, g->ws_bytes);  // ticket counters start at zero
     if (e == cudaSuccess) e = cudaMalloc(&g->curves, (size_t)g->capacity * 2 * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&g->e_current, sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc(&g->e_best, sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&g->e_state, 4 * sizeof(double));
     if (e != cudaSuccess) {
         ggs_sa_destroy(g);
         return fail(e, "ggs_sa_create: cudaMalloc");
@@ -667,8 +677,8 @@ void ggs_sa_destroy(ggs_sa *g)
     if (!g) return;
     DeviceGuard on_device(g->device);
     cudaDeviceSynchronize();
-    void *all[] = {g->current, g->best, g->cand, g->energy, g->dummy_fit, g->target, g->mask, g->ws,
-                   g->curves, g->e_current, g->e_best};
+    void *all[] = {g->current, g->best, g->cand2[0], g->cand2[1], g->energy, g->dummy_fit, g->target,
+                   g->mask, g->ws, g->curves, g->e_state};
     for (void *p : all)
         if (p) cudaFree(p);
     delete g;
@@ -710,21 +720,89 @@ static int sa_energy(ggs_sa *g, const float *genomes, int B, cudaStream_t st, bo
                     nullptr, 0, g->ws, g->ws_bytes, st, opt);
 }
 
-// `count` mutated copies of the current state into g->cand, proposal stream `number`.  When the
-// state fits the proposal kernel (ggs_breed.cu) the children come out decoded as well and the
-// evaluation that follows skips its decode launch; otherwise the general breeding kernel runs.
-static int sa_propose(ggs_sa *g, int count, const float *sigma6, float mutpb, float log_lo, float log_hi,
-                      uint32_t number, cudaStream_t st, bool *decoded)
+// The Metropolis step the pending evaluation is waiting for, as the proposal kernel's judging stage.
+static ProposeJudge sa_judge(ggs_sa *g)
 {
-    *decoded = propose_possible(g->N, 9);
-    if (*decoded) {
-        GGS_TRY(launch_propose(g->current, g->N, 9, count, g->cand, mutpb, sigma6, log_lo, log_hi, g->seed,
-                               number, carve_workspace(g->ws, count, g->N, g->H, g->W), g->H, g->W,
-                               g->k_sigma, st));
-    } else {
-        GGS_TRY(launch_breed(g->current, g->dummy_fit, 1, g->N, 9, count, g->cand, 1, 0.0f, mutpb, sigma6,
-                             log_lo, log_hi, g->seed, number, st));
+    ProposeJudge j;
+    if (!g->pending.on) return j;
+    j.tries = g->pending.tries;
+    j.energy = g->energy;
+    j.cand_prev = g->cand2[g->pending.cand];
+    j.current = g->current;
+    j.best = g->best;
+    j.e_in = g->e_state + 2 * g->ep;
+    j.e_out = g->e_state + 2 * (g->ep ^ 1);
+    j.curve = g->pending.curve;
+    j.temperature = g->pending.temperature;
+    for (int t = 0; t < g->pending.tries; ++t) j.uniform[t] = g->pending.uniform[t];
+    return j;
+}
+
+static MetropolisParams sa_metropolis(ggs_sa *g, const float *cand, int tries, double temperature,
+                                      const double *uniform, double *curve)
+{
+    MetropolisParams q = {};
+    q.cand = cand;
+    q.energy = g->energy;
+    q.current = g->current;
+    q.best = g->best;
+    q.e_current = g->e_state + 2 * g->ep;
+    q.e_best = g->e_state + 2 * g->ep + 1;
+    q.curve = curve;
+    q.temperature = temperature;
+    for (int t = 0; t < tries; ++t) q.uniform[t] = uniform[t];
+    q.tries = tries;
+    q.N = g->N;
+    return q;
+}
+
+// One batch of `count` proposals (mutated copies of the state the chain is in), evaluated, with the
+// Metropolis draws (temperature, uniform[count]) that will judge them and the curve point they
+// belong to.  With a state that fits the proposal kernel (ggs_breed.cu) this is TWO launches:
+// the proposal launch first judges the previous batch, then mutates and decodes, and the raster
+// scores the children; their own judgement is left pending for the next proposal (or for
+// sa_settle).  Larger states take breed + decode + raster + Metropolis.
+static int sa_batch(ggs_sa *g, int count, const float *sigma6, float mutpb, float log_lo, float log_hi,
+                    uint32_t number, double temperature, const double *uniform, double *curve,
+                    cudaStream_t st)
+{
+    if (propose_possible(g->N, 9)) {
+        const ProposeJudge judge = sa_judge(g);
+        const int w = g->cw ^ 1;
+        GGS_TRY(launch_propose(g->current, g->N, 9, count, g->cand2[w], mutpb, sigma6, log_lo, log_hi,
+                               g->seed, number, carve_workspace(g->ws, count, g->N, g->H, g->W), g->H,
+                               g->W, g->k_sigma, judge, st));
+        if (judge.tries > 0) g->ep ^= 1;
+        g->cw = w;
+        int rc = sa_energy(g, g->cand2[w], count, st, /*decoded=*/true);
+        if (rc) return rc;
+        g->pending.on = true;
+        g->pending.tries = count;
+        g->pending.cand = w;
+        g->pending.temperature = temperature;
+        for (int t = 0; t < count; ++t) g->pending.uniform[t] = uniform[t];
+        g->pending.curve = curve;
+        return GGS_OK;
     }
+    GGS_TRY(launch_breed(g->current, g->dummy_fit, 1, g->N, 9, count, g->cand2[0], 1, 0.0f, mutpb, sigma6,
+                         log_lo, log_hi, g->seed, number, st));
+    int rc = sa_energy(g, g->cand2[0], count, st);
+    if (rc) return rc;
+    GGS_TRY(launch_kernel(metropolis_kernel, 1, kSelectThreads, 0, st,
+                          sa_metropolis(g, g->cand2[0], count, temperature, uniform, curve)));
+    return GGS_OK;
+}
+
+// Judge whatever is still pending, so that current / best / energies / curves are final.
+static int sa_settle(ggs_sa *g, cudaStream_t st)
+{
+    if (!g->pending.on) return GGS_OK;
+    const float zero6[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    GGS_TRY(launch_propose(g->current, g->N, 9, 0, g->cand2[g->cw ^ 1], 0.0f, zero6, 0.0f, 0.0f, g->seed, 0,
+                           carve_workspace(g->ws, 1, g->N, g->H, g->W), g->H, g->W, g->k_sigma,
+                           sa_judge(g), st));
+    g->ep ^= 1;
+    g->pending.on = false;
     return GGS_OK;
 }
 
@@ -743,25 +821,18 @@ int ggs_sa_start(ggs_sa *g, const float *d_state, int cols, uint64_t seed, void 
     GGS_TRY(on_device.status());
     // iteration 0: the given state is the current and the best one; its energy opens the curves.
     // It is staged as candidate 0 and "accepted" by the Metropolis kernel (dE = -inf).
-    GGS_TRY(cudaMemcpy2DAsync(g->cand, 9 * sizeof(float), d_state, (size_t)cols * sizeof(float),
+    g->cw = 0;
+    g->ep = 0;
+    g->pending.on = false;
+    GGS_TRY(cudaMemcpy2DAsync(g->cand2[0], 9 * sizeof(float), d_state, (size_t)cols * sizeof(float),
                               9 * sizeof(float), (size_t)g->N, cudaMemcpyDeviceToDevice, st));
-    int rc = sa_energy(g, g->cand, 1, st);
+    int rc = sa_energy(g, g->cand2[0], 1, st);
     if (rc) return rc;
-    const double inf = INFINITY;
-    GGS_TRY(cudaMemcpyAsync(g->e_current, &inf, sizeof(double), cudaMemcpyHostToDevice, st));
-    GGS_TRY(cudaMemcpyAsync(g->e_best, &inf, sizeof(double), cudaMemcpyHostToDevice, st));
-    MetropolisParams q = {};
-    q.cand = g->cand;
-    q.energy = g->energy;
-    q.current = g->current;
-    q.best = g->best;
-    q.e_current = g->e_current;
-    q.e_best = g->e_best;
-    q.curve = g->curves;
-    q.temperature = 0.0;
-    q.tries = 1;
-    q.N = g->N;
-    GGS_TRY(launch_kernel(metropolis_kernel, 1, kSelectThreads, 0, st, q));
+    const double inf2[2] = {INFINITY, INFINITY};
+    GGS_TRY(cudaMemcpyAsync(g->e_state, inf2, sizeof(inf2), cudaMemcpyHostToDevice, st));
+    const double no_draw = 0.0;
+    GGS_TRY(launch_kernel(metropolis_kernel, 1, kSelectThreads, 0, st,
+                          sa_metropolis(g, g->cand2[0], 1, 0.0, &no_draw, g->curves)));
     g->seed = seed;
     g->iteration = 0;
     return GGS_OK;
@@ -789,49 +860,30 @@ int ggs_sa_run(ggs_sa *g, int count, const float *h_sigma6, const double *h_temp
     GGS_TRY(on_device.status());
     for (int k = 0; k < count; ++k) {
         const int it = g->iteration + 1;
-        MetropolisParams q = {};
-        q.cand = g->cand;
-        q.energy = g->energy;
-        q.current = g->current;
-        q.best = g->best;
-        q.e_current = g->e_current;
-        q.e_best = g->e_best;
-        q.curve = g->curves + (size_t)it * 2;
-        q.temperature = h_temperature[k];
-        q.N = g->N;
+        double *curve = g->curves + (size_t)it * 2;
+        const float *sigma6 = h_sigma6 + 6 * (size_t)k;
+        const double *uniform = h_uniform + (size_t)k * g->tries;
         if (g->sequential) {
             // The reference's chain (annealing.py:121-146): every try mutates the state the previous
             // try left behind, is evaluated on its own (B = 1: the raster's 8-way split) and is
             // accepted or rejected before the next one is proposed.  Proposal number
             // (it - 1) * tries + t + 1 keys the random stream, as in the Python-driven loop.
             for (int t = 0; t < g->tries; ++t) {
-                bool decoded = false;
-                int rc = sa_propose(g, 1, h_sigma6 + 6 * (size_t)k, mutpb, log_scale_lo, log_scale_hi,
-                                    (uint32_t)((size_t)(it - 1) * g->tries + t + 1), st, &decoded);
+                int rc = sa_batch(g, 1, sigma6, mutpb, log_scale_lo, log_scale_hi,
+                                  (uint32_t)((size_t)(it - 1) * g->tries + t + 1), h_temperature[k],
+                                  uniform + t, curve, st);
                 if (rc) return rc;
-                rc = sa_energy(g, g->cand, 1, st, decoded);
-                if (rc) return rc;
-                q.uniform[0] = h_uniform[(size_t)k * g->tries + t];
-                q.tries = 1;
-                GGS_TRY(launch_kernel(metropolis_kernel, 1, kSelectThreads, 0, st, q));
             }
         } else {
-            // `tries` independently mutated copies of the current state: the breeding kernel with a
-            // one-individual population and no crossover (annealing.py:121-128, batched), one
-            // evaluation of all of them, the Metropolis tests applied in order
-            bool decoded = false;
-            int rc = sa_propose(g, g->tries, h_sigma6 + 6 * (size_t)k, mutpb, log_scale_lo, log_scale_hi,
-                                (uint32_t)it, st, &decoded);
+            // `tries` independently mutated copies of the current state (annealing.py:121-128,
+            // batched), one evaluation of all of them, the Metropolis tests applied in order
+            int rc = sa_batch(g, g->tries, sigma6, mutpb, log_scale_lo, log_scale_hi, (uint32_t)it,
+                              h_temperature[k], uniform, curve, st);
             if (rc) return rc;
-            rc = sa_energy(g, g->cand, g->tries, st, decoded);
-            if (rc) return rc;
-            for (int t = 0; t < g->tries; ++t) q.uniform[t] = h_uniform[(size_t)k * g->tries + t];
-            q.tries = g->tries;
-            GGS_TRY(launch_kernel(metropolis_kernel, 1, kSelectThreads, 0, st, q));
         }
         g->iteration = it;
     }
-    return GGS_OK;
+    return sa_settle(g, st);  // the last batch's verdict: the state is final when this call returns
 }
 
 int ggs_sa_set_mode(ggs_sa *g, int batched_neighbours)
@@ -861,9 +913,11 @@ int ggs_sa_state(ggs_sa *g, void *stream, int *h_iteration, double *h_best_energ
     GGS_TRY(on_device.status());
     const size_t row = (size_t)g->N * 9 * sizeof(float);
     if (h_best_energy)
-        GGS_TRY(cudaMemcpyAsync(h_best_energy, g->e_best, sizeof(double), cudaMemcpyDeviceToHost, st));
+        GGS_TRY(cudaMemcpyAsync(h_best_energy, g->e_state + 2 * g->ep + 1, sizeof(double),
+                                cudaMemcpyDeviceToHost, st));
     if (h_current_energy)
-        GGS_TRY(cudaMemcpyAsync(h_current_energy, g->e_current, sizeof(double), cudaMemcpyDeviceToHost, st));
+        GGS_TRY(cudaMemcpyAsync(h_current_energy, g->e_state + 2 * g->ep, sizeof(double),
+                                cudaMemcpyDeviceToHost, st));
     if (h_curves2 && curves_from <= g->iteration)
         GGS_TRY(cudaMemcpyAsync(h_curves2, g->curves + (size_t)curves_from * 2,
                                 (size_t)(g->iteration + 1 - curves_from) * 2 * sizeof(double),

@@ -193,10 +193,12 @@ def host_sa_iteration(ggs, cur, e_cur, best, e_best, t, m, H, W, tries, it, seed
 
 
 @pytest.mark.parametrize("batched", [True, False])
-@pytest.mark.parametrize("N,tries,T0", [(40, 8, 2e-3), (33, 1, 1e-3), (12, 64, 5e-3), (25, 5, 0.0)])
+@pytest.mark.parametrize("N,tries,T0", [(40, 8, 2e-3), (33, 1, 1e-3), (12, 64, 5e-3), (25, 5, 0.0),
+                                        (1, 3, 1e-3),       # one splat: no swap, every group forced
+                                        (4200, 2, 1e-3)])   # beyond the proposal kernel: breed + decode
 def test_sa_engine_iterations_match_host_metropolis(ggs, N, tries, T0, batched):
     from ggs_b200.engine import SaEngine
-    H, W, I, seed = 48, 64, 14 if batched or tries < 64 else 4, 31
+    H, W, I, seed = 48, 64, (14 if batched or tries < 64 else 4) if N < 1000 else 3, 31
     pop, t, m = setup(1, N, H, W, seed=N)
     rng = np.random.default_rng(tries)
     eng = SaEngine(t, m, H, W, N, tries, I, batch_neighbors=batched)
