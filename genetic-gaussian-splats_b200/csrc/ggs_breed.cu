@@ -557,35 +557,32 @@ __global__ void __launch_bounds__(kProposeThreads) propose_kernel(const __grid_c
         s_judged_cur = cur;
         s_judged_best = best;
     }
-    __syncthreads();
+    // (no barrier yet: the verdict is needed from pass 2 on, and the mask pass below does not
+    // depend on it -- thread 0's loads overlap the other threads' Philox work)
     const int64_t row_floats = (int64_t)q.N * 9;
-    const float *parent = q.pop;  // the current state ...
-    int parent_cols = q.cols;
-    if (s_judged_cur >= 0) {      // ... unless a candidate of the previous batch was accepted
-        parent = J.cand_prev + s_judged_cur * row_floats;
-        parent_cols = 9;
-    }
-    if (blockIdx.x == 0 && J.tries > 0) {  // nobody reads `current` when it is being replaced
-        if (s_judged_best >= 0)
+    if (q.n_children == 0) {  // a judging-only launch: move the rows and leave
+        __syncthreads();
+        if (J.tries > 0 && s_judged_best >= 0)
             for (int64_t i = tid; i < row_floats; i += kProposeThreads)
                 J.best[i] = J.cand_prev[s_judged_best * row_floats + i];
-        if (s_judged_cur >= 0)
-            for (int64_t i = tid; i < row_floats; i += kProposeThreads) J.current[i] = parent[i];
+        if (J.tries > 0 && s_judged_cur >= 0)
+            for (int64_t i = tid; i < row_floats; i += kProposeThreads)
+                J.current[i] = J.cand_prev[s_judged_cur * row_floats + i];
+        return;
     }
-    if (q.n_children == 0) return;  // a judging-only launch
 
-    if (tid < 4) {
-        s_count[tid] = 0;
-        s_force[tid] = -1;
+    // the set-up belongs to warp 1, so that thread 0 (still judging) is not on its way
+    if (tid >= 32 && tid < 36) {
+        s_count[tid - 32] = 0;
+        s_force[tid - 32] = -1;
     }
-    if (tid == 0) {
+    if (tid == 36) {
         s_best = 0ull;
         const U4 r = philox4x32_10(q.gen, child, 0, kSwapIdx, q.seed_lo, q.seed_hi);
         s_swap_i = (q.N >= 2) ? (int)__umulhi(r.x, (unsigned)(q.N - 1)) : 0;
         s_swap_salt = r.y;
         p.counters[child] = 0;
     }
-    __syncthreads();
 
     // pass 1: the masks, and how many genes of each group mutate ("at least one" rule)
     int cnt[4] = {0, 0, 0, 0};
@@ -597,6 +594,7 @@ __global__ void __launch_bounds__(kProposeThreads) propose_kernel(const __grid_c
         cnt[2] += __popc(m & 16u);
         cnt[3] += __popc(m & 96u);
     }
+    __syncthreads();  // the counters are cleared, the verdict is in
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         int v = cnt[g];
@@ -612,14 +610,37 @@ __global__ void __launch_bounds__(kProposeThreads) propose_kernel(const __grid_c
     }
     __syncthreads();
 
-    // pass 2: mutation and projection of every row, into shared memory
+    // pass 2: mutation and projection of every row, into shared memory.  The parent is the
+    // current state unless the verdict accepted a candidate of the previous batch; CTA 0 records
+    // the accepted rows as the new current (and best) state on the way -- nobody reads `current`
+    // when it is being replaced.
     const int f0 = s_force[0], f1 = s_force[1], f2 = s_force[2], f3 = s_force[3];
     const int swap_i = s_swap_i;
+    const int j_cur = s_judged_cur, j_best = s_judged_best;
+    const float *parent = q.pop;
+    int parent_cols = q.cols;
+    if (j_cur >= 0) {
+        parent = J.cand_prev + j_cur * row_floats;
+        parent_cols = 9;
+    }
+    const bool keep_cur = (blockIdx.x == 0 && j_cur >= 0);
+    const bool keep_best = (blockIdx.x == 0 && j_best >= 0 && j_best == j_cur);
+    if (blockIdx.x == 0 && j_best >= 0 && j_best != j_cur)  // the best was an earlier accepted try
+        for (int64_t i = tid; i < row_floats; i += kProposeThreads)
+            J.best[i] = J.cand_prev[j_best * row_floats + i];
     for (int n = tid; n < q.N; n += kProposeThreads) {
         const float *src = parent + (int64_t)n * parent_cols;
         float g[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) g[k] = src[k];
+        if (keep_cur) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) J.current[(int64_t)n * 9 + k] = g[k];
+        }
+        if (keep_best) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) J.best[(int64_t)n * 9 + k] = g[k];
+        }
         unsigned m = s_mask[n] & kFlagBits;
         if (f0 >= 0 && (f0 >> 1) == n) m |= 1u << (f0 & 1);
         if (f1 >= 0 && (f1 >> 1) == n) m |= 4u << (f1 & 1);
