@@ -267,6 +267,19 @@ int ggs_fitness_allgather(ggs_peers *p, const float *d_genomes, int layout, int 
         set_error("ggs_fitness_allgather: bad arguments");
         return GGS_EINVAL;
     }
+    if ((layout != GGS_LAYOUT_AXES_ANGLE && layout != GGS_LAYOUT_CHOLESKY) || H < 1 || W < 1 ||
+        H > GGS_MAX_SIDE || W > GGS_MAX_SIDE) {
+        set_error("ggs_fitness_allgather: bad layout or image size");
+        return GGS_EINVAL;
+    }
+    // everything that can fail is checked BEFORE an epoch is taken: a rank that takes one and then
+    // does not deliver would leave its peers waiting for the time-out
+    if (B > 0 && (d_workspace == nullptr || workspace_bytes_given < workspace_bytes(B, N, H, W) ||
+                  (reinterpret_cast<uintptr_t>(d_workspace) & 255u) != 0)) {
+        set_error("ggs_fitness_allgather: workspace missing, misaligned or smaller than %zu bytes",
+                  workspace_bytes(B, N, H, W));
+        return GGS_EWORKSPACE;
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     DeviceGuard on_device(p->device);
     GGS_TRY(on_device.status());
