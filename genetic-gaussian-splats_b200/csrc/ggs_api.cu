@@ -26,6 +26,8 @@ void set_error(const char *fmt, ...)
 struct Options {
     int pdl;    // programmatic dependent launch between the kernels of a step (GGS_B200_PDL, default 1)
     int split;  // CTAs per (candidate, tile): 0 = automatic (GGS_B200_SPLIT)
+    int tile_order;  // 1 (default): grids of one to four waves start the image's interior tiles first
+                     // (GGS_B200_TILE_ORDER); 0: candidate-major always.  Results do not depend on it.
     int fuse;   // decode fused into the raster: 0 = never (default), 1 = whenever a segment fits the
                 // list, -1 = when the grid is a single wave and it fits (GGS_B200_FUSE).  Measured on
                 // the B200 the fused variant never wins: every CTA pays the decode's chain of
@@ -39,7 +41,8 @@ static int env_int(const char *name, int fallback)
 }
 static Options &options()
 {
-    static Options o = {env_int("GGS_B200_PDL", 1) != 0, env_int("GGS_B200_SPLIT", 0), env_int("GGS_B200_FUSE", 0)};
+    static Options o = {env_int("GGS_B200_PDL", 1) != 0, env_int("GGS_B200_SPLIT", 0),
+                        env_int("GGS_B200_TILE_ORDER", 1), env_int("GGS_B200_FUSE", 0)};
     return o;
 }
 
@@ -225,6 +228,10 @@ int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, 
     const int fuse = stats ? 0 : (opt.fuse >= 0 ? opt.fuse : options().fuse);
     const int64_t ctas = (int64_t)B * tiles_x(W) * tiles_y(H) * q.split;
     q.small_grid = ctas <= wave_slots();
+    // measured (tools/time_cta_order.py): 4-9 % on grids of one to four waves, a loss on deep
+    // genomes, where saturation and not the list length decides what a tile costs
+    q.interior_first = options().tile_order != 0 && N <= 1536 && ctas > wave_slots() &&
+                       ctas <= 4 * (int64_t)wave_slots();
     q.fused = !opt.decoded && N > 0 && fuse != 0 && fused_decode_possible(N, q.split) &&
               (fuse == 1 || q.small_grid);
 
@@ -654,6 +661,8 @@ int ggs_set_option(const char *name, int value)
         options().split = value;
     } else if (name != nullptr && strcmp(name, "fuse") == 0 && value >= -1 && value <= 1) {
         options().fuse = value;
+    } else if (name != nullptr && strcmp(name, "tile_order") == 0 && (value == 0 || value == 1)) {
+        options().tile_order = value;
     } else {
         set_error("ggs_set_option: unknown option or value (%s = %d)", name ? name : "(null)", value);
         return GGS_EINVAL;

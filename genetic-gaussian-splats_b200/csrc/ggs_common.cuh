@@ -103,6 +103,7 @@ struct RasterLaunch {
     int split = 1;        // CTAs per (candidate, tile): 1, 2, 4 or 8
     bool fused = false;   // decode inside the raster (needs the genomes, ceil(N / split) <= kListCap)
     bool small_grid = false;  // at most one wave of CTAs: latency matters more than L1 traffic
+    bool interior_first = false;  // one to a few waves: start the expensive (interior) tiles first
     const float *d_genomes = nullptr;
     int layout = GGS_LAYOUT_AXES_ANGLE, cols = 9;
     float k_sigma = 3.0f;

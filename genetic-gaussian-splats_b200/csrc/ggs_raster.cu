@@ -404,21 +404,54 @@ struct RasterArgs {
     unsigned long long *stats;
     int split;  // CTAs per (candidate, tile): the cluster size of raster_split_kernel
     int prefetch_inputs;  // latency regime: pull the tile's target / mask lines into L1 up front
+    int B;                // candidates of this launch
     PeerStores peers;  // fitness stores into the other GPUs' gathered vectors (ggs_peers.cu)
 };
 
 struct TileGeom {
-    int b, X0, Y0, X1, Y1, X, Yb;
+    int b, t, X0, Y0, X1, Y1, X, Yb;
     float Xf, Ybf;
     unsigned lanebit, band_sel;
 };
 
-__device__ __forceinline__ TileGeom tile_geometry(int cand_tile, int ntx, int ntiles, int lane, int warp)
+// CTA index -> (candidate, tile).  Candidate-major by default: the tiles of a candidate run
+// together and share its records in L1 / L2.  `interior_first` (grids of one to a few waves, where
+// the LAST wave decides the launch time): tile-major with the image's interior tiles ahead of its
+// border tiles, so that the CTAs that start last are the cheap ones -- a border tile lists about
+// 60 % of the splats of an interior one.  Results do not depend on the order (partials are stored
+// and summed by tile index).
+template <bool kInteriorFirst = false>
+__device__ __forceinline__ TileGeom tile_geometry(int cand_tile, int ntx, int ntiles, int lane, int warp,
+                                                  int B = 1)
 {
     TileGeom g;
-    g.b = cand_tile / ntiles;
-    const int t = cand_tile - g.b * ntiles;
-    const int ty = t / ntx, tx = t - ty * ntx;
+    int tx, ty;
+    if (kInteriorFirst) {
+        const int nty = ntiles / ntx, wi = ntx - 2, n_int = wi * (nty - 2);
+        const int r = cand_tile / B;
+        g.b = cand_tile - r * B;
+        if (r < n_int) {
+            ty = 1 + r / wi;
+            tx = 1 + r - (ty - 1) * wi;
+        } else {
+            int k = r - n_int;  // the border, ring-wise: top row, bottom row, left and right columns
+            if (k < ntx) {
+                ty = 0, tx = k;
+            } else if (k < 2 * ntx) {
+                ty = nty - 1, tx = k - ntx;
+            } else {
+                k -= 2 * ntx;
+                ty = 1 + (k >> 1);
+                tx = (k & 1) ? ntx - 1 : 0;
+            }
+        }
+    } else {
+        g.b = cand_tile / ntiles;
+        const int t = cand_tile - g.b * ntiles;
+        ty = t / ntx;
+        tx = t - ty * ntx;
+    }
+    g.t = ty * ntx + tx;
     g.X0 = tx * kTileW;
     g.Y0 = ty * kTileH;
     g.X1 = g.X0 + kTileW - 1;
@@ -645,7 +678,7 @@ __device__ __forceinline__ void emit_pixel(const RasterArgs &a, int b, int X, in
 // applies the mode formula: fitness is bit-reproducible.  Deliberately NOT inlined: it runs once
 // per CTA, and with its body (and the peer stores) inside the kernel ptxas moved the composite
 // loop's list address out of the uniform registers.
-__device__ __noinline__ void reduce_and_finish(const RasterArgs &a, int b, int per_cand, float num,
+__device__ __noinline__ void reduce_and_finish(const RasterArgs &a, int b, int slot, int per_cand, float num,
                                                float den, const RasterSmem &sm, int tid, int lane, int warp)
 {
 #pragma unroll
@@ -667,7 +700,7 @@ __device__ __noinline__ void reduce_and_finish(const RasterArgs &a, int b, int p
             n += sm.red[w];
             d += sm.red[kWarps + w];
         }
-        a.partial[blockIdx.x] = make_float2(n, d);
+        a.partial[(int64_t)b * per_cand + slot] = make_float2(n, d);  // by tile, whatever the CTA order
         // release our partial, acquire everybody else's: one acq_rel RMW instead of fence + atomic
         asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(ticket) : "l"(a.counter + b) : "memory");
     }
@@ -736,13 +769,15 @@ __device__ __forceinline__ void prefetch_tile_inputs(const RasterArgs &a, const 
                 (g.X < a.W && g.Yb + 2 * k + 1 < a.H) ? 1.0f : 0.0f)
 
 // ---- throughput path: one CTA per (candidate, tile) -------------------------------------------
-template <bool kStats>
+// kInteriorFirst is a template parameter, not an argument: with both orders in one instance the
+// throughput kernel (config 3) lost 1.7 % to the extra prologue code and its spills.
+template <bool kStats, bool kInteriorFirst>
 __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_kernel(const __grid_constant__ RasterArgs a)
 {
     unsigned work[2] = {0u, 0u};  // kStats: row pairs blended on the recurrence / exact path
     GGS_SMEM_DECLARE();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TileGeom g = tile_geometry(blockIdx.x, a.ntx, a.ntiles, lane, warp);
+    const TileGeom g = tile_geometry<kInteriorFirst>(blockIdx.x, a.ntx, a.ntiles, lane, warp, a.B);
 
     GGS_PX_DECLARE();
     GGS_PAIRS(GGS_T_INIT)
@@ -790,7 +825,7 @@ __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_kernel(const 
         atomicAdd(a.stats + 1, (unsigned long long)work[1]);
     }
     if (a.target == nullptr) return;
-    reduce_and_finish(a, g.b, a.ntiles, num, den, sm, tid, lane, warp);
+    reduce_and_finish(a, g.b, g.t, a.ntiles, num, den, sm, tid, lane, warp);
 }
 
 // ---- latency path: a cluster of `split` CTAs per (candidate, tile) ----------------------------
@@ -868,7 +903,7 @@ __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_split_kernel(
     }
     cluster.sync();  // nobody leaves while a neighbour still reads its shared memory
     if (a.target == nullptr) return;
-    reduce_and_finish(a, g.b, a.ntiles * K, num, den, sm, tid, lane, warp);
+    reduce_and_finish(a, g.b, g.t * K + k, a.ntiles * K, num, den, sm, tid, lane, warp);
 }
 #undef GGS_READ_ALL
 #undef GGS_T_INIT
@@ -915,6 +950,8 @@ cudaError_t launch_raster(const RasterLaunch &q, cudaStream_t stream)
     a.stats = q.d_stats;
     a.split = split;
     a.prefetch_inputs = q.small_grid ? 1 : 0;
+    a.B = q.B;
+    const bool interior_first = q.interior_first && split == 1 && ntx >= 3 && ntiles / ntx >= 3;
     a.peers = q.peers;
     if (q.fused) {
         if (!fused_decode_possible(q.N, split)) return cudaErrorInvalidConfiguration;
@@ -923,8 +960,11 @@ cudaError_t launch_raster(const RasterLaunch &q, cudaStream_t stream)
         return launch_kernel_cluster(raster_split_kernel<2>, (unsigned)grid, kThreads, 0, split, stream, a);
     }
     if (split > 1) return launch_kernel_cluster(raster_split_kernel<0>, (unsigned)grid, kThreads, 0, split, stream, a);
-    if (q.d_stats != nullptr) return launch_kernel(raster_kernel<true>, (unsigned)grid, kThreads, 0, stream, a);
-    return launch_kernel(raster_kernel<false>, (unsigned)grid, kThreads, 0, stream, a);
+    if (q.d_stats != nullptr)
+        return launch_kernel(raster_kernel<true, false>, (unsigned)grid, kThreads, 0, stream, a);
+    if (interior_first)
+        return launch_kernel(raster_kernel<false, true>, (unsigned)grid, kThreads, 0, stream, a);
+    return launch_kernel(raster_kernel<false, false>, (unsigned)grid, kThreads, 0, stream, a);
 }
 
 }  // namespace ggs

@@ -145,6 +145,9 @@ int ggs_fitness_ex(const float *d_genomes, int layout, int B, int N, int cols, i
  * between the kernels of a step.  "split" (GGS_B200_SPLIT, default 0 = automatic): force 1, 2, 4
  * or 8 wherever the caller does not pass one.  "fuse" (GGS_B200_FUSE, default 0 = never): 1 = decode
  * inside the raster launch whenever a segment fits the list, -1 = only for single-wave grids.
+ * "tile_order" (GGS_B200_TILE_ORDER, default 1): grids of one to four waves launch the image's
+ * interior tiles ahead of its border tiles (the last wave is then made of the cheap ones); 0 =
+ * candidate-major always.  Results are bit-identical either way.
  */
 int ggs_set_option(const char *name, int value);
 

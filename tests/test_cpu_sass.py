@@ -27,8 +27,8 @@ def production_kernel_sass():
         mod.build()
     text = subprocess.run(["cuobjdump", "-sass", OBJ], capture_output=True, text=True, check=True).stdout
     funcs = re.split(r"\n\s*Function : ", text)
-    prod = [f for f in funcs if "raster_kernelILb0E" in f.split("\n", 1)[0]]
-    assert len(prod) == 1, "raster_kernel<false> not found in the object"
+    prod = [f for f in funcs if "raster_kernelILb0ELb0E" in f.split("\n", 1)[0]]
+    assert len(prod) == 1, "raster_kernel<false, false> not found in the object"
     ops = []
     for line in prod[0].splitlines():
         m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?)\s*;", line)

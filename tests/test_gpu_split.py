@@ -128,6 +128,24 @@ def test_automatic_split_policy(ggs):
         ggs.fitness(g, t, 128, 128, 3.0, split=5)
 
 
+def test_cta_order_does_not_change_a_bit(ggs):
+    """Grids of one to four waves run tile-major, interior tiles first; partial sums are stored and
+    added by tile index, so images and fitness are those of the candidate-major order."""
+    from ggs_b200 import synth
+    for (B, N, H, W) in ((30, 300, 256, 256), (24, 512, 256, 256), (70, 90, 200, 136), (5, 400, 512, 512)):
+        g = cuda(synth.new_population_np(B, N, H, W, seed=B))
+        t = cuda(synth.synthetic_target_np(H, W, B))
+        m = cuda(np.random.default_rng(B).uniform(0.2, 1.0, size=(H, W)).astype(np.float32))
+        out = {}
+        for order in (1, 0):
+            ggs.set_option("tile_order", order)
+            out[order] = ggs.fitness(g, t, H, W, 3.0, weight_mask=m, want_images=True)
+        ggs.set_option("tile_order", 1)
+        assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1]), (B, N, H, W)
+        f_cpu = oracle.fitness(g.cpu().numpy(), t.cpu().numpy(), H, W, 3.0, weight_mask=m.cpu().numpy())
+        np.testing.assert_allclose(out[1][0].cpu().numpy(), f_cpu, rtol=FIT_RTOL)
+
+
 def test_host_path_and_render_entries_on_the_small_batch_path(ggs):
     from ggs_b200 import synth
     B, N, H, W = 3, 200, 128, 128

@@ -11,7 +11,7 @@ BASE = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17
 def analyse(obj):
     text = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
     funcs = re.split(r"\n\s*Function : ", text)
-    prod = [f for f in funcs if "raster_kernelILb0E" in f.split("\n", 1)[0]][0]
+    prod = [f for f in funcs if "raster_kernelILb0ELb0E" in f.split("\n", 1)[0]][0]
     ops = [m.group(1) for m in (re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?)\s*;", l) for l in prod.splitlines()) if m]
     first = next(i for i, o in enumerate(ops) if "MUFU.EX2" in o)
     end = next(i for i in range(first, len(ops)) if re.match(r"(@!?U?P\d+\s+)?BRA\b", ops[i]))

@@ -9,7 +9,7 @@ out = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True
 fn, keep = [], False
 for line in out.splitlines():
     if "Function :" in line:
-        keep = "raster_kernelILb0" in line
+        keep = "raster_kernelILb0ELb0E" in line
     if keep and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
         fn.append(re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", line))
 first_mufu = next(i for i, l in enumerate(fn) if "MUFU.EX2" in l)
