@@ -521,15 +521,16 @@ int ggs_ctx_fitness_host(ggs_ctx *c, const float *h_genomes, int layout, int B, 
     GGS_CUDA(on_device.status());
 
     // The genomes go up in slices on a copy stream that runs ahead of the compute streams;
-    // slice k is evaluated as soon as it has landed.  Sizes double (B/16, B/8, B/4, rest), so
-    // only a sixteenth of the copy is exposed and every later copy hides behind the previous,
+    // slice k is evaluated as soon as it has landed.  Sizes double (B/64, B/32, B/16, B/8, rest),
+    // so only a sixty-fourth of the copy is exposed and every later copy hides behind the previous,
     // smaller, evaluation; consecutive slices use alternating compute streams so the tail of
-    // one raster overlaps the head of the next.
+    // one raster overlaps the head of the next.  (Measured at config 3: first slice B/16 with
+    // four slices 3.200 ms per call, B/32 3.173, B/64 with five slices 3.166, B/128 3.175.)
     int start[kMaxSlices + 1];
     int ns = 0;
     start[0] = 0;
-    for (int sz = std::max(32, B / 16); start[ns] < B && ns < kMaxSlices; sz *= 2) {
-        const bool last = (ns == 3) || (ns == kMaxSlices - 1) || start[ns] + sz >= B;
+    for (int sz = std::max(16, B / 64); start[ns] < B && ns < kMaxSlices; sz *= 2) {
+        const bool last = (ns == 4) || (ns == kMaxSlices - 1) || start[ns] + sz >= B;
         start[ns + 1] = last ? B : start[ns] + sz;
         ++ns;
     }
