@@ -456,6 +456,14 @@ def run_ours(args, wl):
     ggs_b200.lib()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
+    if world > 1 and args.numa_bind:
+        # one process per GPU: run, and first-touch the pinned genome buffers of the e2e leg, on the
+        # socket this GPU hangs off.  Opt-in: the GPU pool's boxes are single-node VMs (nvidia-smi
+        # topo: one NUMA node, 32 CPUs), where there is nothing to choose.
+        from ggs_b200.numa import bind_to_device
+        numa = bind_to_device(local_rank)
+        log(f"[bench] rank {rank}: NUMA node {numa['node']}, bound to {numa['cpus']} CPUs: {numa['bound']}")
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -677,6 +685,7 @@ def run_ours(args, wl):
                                "nccl": "dist.all_gather_into_tensor after the evaluation",
                                "none": "single GPU"}[gather], "kind": gather},
             "gather_bit_identical": gather_ok,
+            "numa": numa,
             "extra": {"config4": c4},
         }
         emit(line)
@@ -697,6 +706,9 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference", "reference-gpu-child"], default="ours")
     ap.add_argument("--gather", choices=["p2p", "nccl"], default="p2p",
                     help="N > 1: how the fitness vector reaches every rank")
+    ap.add_argument("--numa-bind", action="store_true",
+                    help="N > 1: pin each rank to the CPUs of its GPU's NUMA node before the pinned host "
+                         "buffers of the e2e leg are allocated (multi-socket hosts)")
     ap.add_argument("--no-config4", action="store_true",
                     help="skip the BASELINE config 4 leg (512x512, 4,000 splats, P = 8,192 over N GPUs)")
     ap.add_argument("--no-reference-gpu", action="store_true",
