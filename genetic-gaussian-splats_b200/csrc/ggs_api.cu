@@ -552,8 +552,12 @@ int ggs_ctx_fitness_host(ggs_ctx *c, const float *h_genomes, int layout, int B, 
     // not depend on how the batch is sliced and equals ggs_fitness on the same genomes.
     EvalOptions opt;
     opt.split = choose_split(B, N, c->H, c->W);
-    opt.fuse = (fused_decode_possible(N, opt.split) &&
-                (int64_t)B * tiles_x(c->W) * tiles_y(c->H) * opt.split <= wave_slots()) ? 1 : 0;
+    // evaluate()'s own rule (option `fuse`: 0 = never, the default; 1 = whenever a segment fits;
+    // -1 = on single-wave grids), applied to the whole batch instead of slice by slice
+    const int fuse_option = options().fuse;
+    opt.fuse = (fuse_option != 0 && fused_decode_possible(N, opt.split) &&
+                (fuse_option == 1 ||
+                 (int64_t)B * tiles_x(c->W) * tiles_y(c->H) * opt.split <= wave_slots())) ? 1 : 0;
     opt.counters_zeroed = true;
     for (int k = 0; k < ns; ++k) {
         const size_t off = (size_t)start[k] * N * cols;

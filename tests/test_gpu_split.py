@@ -165,6 +165,22 @@ def test_host_path_and_render_entries_on_the_small_batch_path(ggs):
     assert np.array_equal(u8, (img * 255.0).astype("uint8"))
 
 
+@pytest.mark.parametrize("B,N,H,W", [(32, 100, 128, 128), (64, 100, 128, 128), (8, 500, 256, 256),
+                                     (16, 100, 128, 128), (24, 512, 256, 256), (1, 500, 256, 256)])
+def test_host_path_equals_device_path_on_grids_of_at_most_a_few_waves(ggs, B, N, H, W):
+    # the sliced host-buffer entry picks split, decode fusion and CTA order from the WHOLE batch:
+    # same bits as one ggs_fitness call (BASELINE configs 1 and 2, the default GA's children, one try)
+    from ggs_b200 import synth
+    g = synth.new_population_np(B, N, H, W, seed=5)
+    t = synth.synthetic_target_np(H, W, 5)
+    m = synth.importance_mask_np(t)
+    dev = ggs.fitness(cuda(g), cuda(t), H, W, 3.0, weight_mask=cuda(m)).cpu().numpy()
+    he = ggs.HostEvaluator(t, m)
+    assert np.array_equal(he.fitness(g), dev)
+    assert np.array_equal(he.fitness(g), dev)
+    he.close()
+
+
 def test_small_batch_path_in_a_cuda_graph(ggs):
     # cluster launches and the counter memset of the fused path are capturable
     from ggs_b200 import synth
