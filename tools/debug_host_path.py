@@ -1,3 +1,6 @@
+"""Host-buffer entry (ggs_ctx_fitness_host) against the device entry (ggs_fitness) on the same genomes,
+bit for bit, over batch sizes from one try to a full population; prints which split of the device
+entry the host path equals.   gpurun -- python tools/debug_host_path.py"""
 import sys, numpy as np, torch
 sys.path.insert(0, "genetic-gaussian-splats_b200")
 import ggs_b200
