@@ -26,7 +26,7 @@ void set_error(const char *fmt, ...)
 struct Options {
     int pdl;    // programmatic dependent launch between the kernels of a step (GGS_B200_PDL, default 1)
     int split;  // CTAs per (candidate, tile): 0 = automatic (GGS_B200_SPLIT)
-    int tile_order;  // 1 (default): grids of one to four waves start the image's interior tiles first
+    int tile_order;  // 1 (default): grids between two CTAs per SM and four waves run the tiles centre-out
                      // (GGS_B200_TILE_ORDER); 0: candidate-major always.  Results do not depend on it.
     int fuse;   // decode fused into the raster: 0 = never (default), 1 = whenever a segment fits the
                 // list, -1 = when the grid is a single wave and it fits (GGS_B200_FUSE).  Measured on
@@ -230,7 +230,10 @@ int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, 
     q.small_grid = ctas <= wave_slots();
     // measured (tools/time_cta_order.py): 4-9 % on grids of one to four waves, a loss on deep
     // genomes, where saturation and not the list length decides what a tile costs
-    q.interior_first = options().tile_order != 0 && N <= 1536 && ctas > wave_slots() &&
+    // and 8-12 % on grids of LESS than a wave with more than one CTA per SM: the block scheduler
+    // deals CTAs to the SMs in index order, so heavy tiles first means the SMs that get one CTA more
+    // than the others get a light one (tools/time_cta_order_small.py)
+    q.interior_first = options().tile_order != 0 && N <= 1536 && ctas > wave_slots() / 8 &&
                        ctas <= 4 * (int64_t)wave_slots();
     q.fused = !opt.decoded && N > 0 && fuse != 0 && fused_decode_possible(N, q.split) &&
               (fuse == 1 || q.small_grid);
@@ -672,6 +675,16 @@ int ggs_set_option(const char *name, int value)
         set_error("ggs_set_option: unknown option or value (%s = %d)", name ? name : "(null)", value);
         return GGS_EINVAL;
     }
+    return GGS_OK;
+}
+
+int ggs_tile_order(int ntx, int nty, int *out_xy)
+{
+    if (ntx < 1 || nty < 1 || out_xy == nullptr) {
+        set_error("ggs_tile_order: bad arguments (ntx=%d nty=%d)", ntx, nty);
+        return GGS_EINVAL;
+    }
+    for (int r = 0; r < ntx * nty; ++r) centre_out_tile(r, ntx, nty, out_xy[2 * r], out_xy[2 * r + 1]);
     return GGS_OK;
 }
 

@@ -75,6 +75,38 @@ struct PeerStores {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Tile of rank r in centre-out order (the CTA order of grids between two CTAs per SM and four
+// waves, ggs_raster.cu): ring after ring from the innermost, and inside a ring the edge cells
+// ahead of its four corners.  Ring k = the cells at distance k from the image border; a tile nearer
+// the border is overlapped by fewer splats.  A permutation of the ntx x nty tiles for every size.
+__host__ __device__ inline void centre_out_tile(int r, int ntx, int nty, int &tx, int &ty)
+{
+    int k = ((ntx < nty ? ntx : nty) - 1) >> 1;  // innermost ring
+    int inner = 0;                               // cells strictly inside ring k
+    for (; k > 0; --k) {
+        const int here = (ntx - 2 * k) * (nty - 2 * k);
+        if (r < here) break;
+        inner = here;
+    }
+    const int w = ntx - 2 * k, h = nty - 2 * k;
+    int j = r - inner;  // position inside ring k (a w x h frame at offset (k, k))
+    if (w == 1 || h == 1) {  // a line, not a frame
+        tx = k + (h == 1 ? j : 0);
+        ty = k + (h == 1 ? 0 : j);
+    } else if (j < 2 * (w - 2)) {  // top and bottom edges without their corners
+        const int top = j < w - 2;
+        tx = k + 1 + (top ? j : j - (w - 2));
+        ty = top ? k : k + h - 1;
+    } else if ((j -= 2 * (w - 2)) < 2 * (h - 2)) {  // left and right edges without their corners
+        tx = (j & 1) ? k + w - 1 : k;
+        ty = k + 1 + (j >> 1);
+    } else {  // the four corners
+        j -= 2 * (h - 2);
+        tx = (j & 1) ? k + w - 1 : k;
+        ty = (j & 2) ? k + h - 1 : k;
+    }
+}
+
 inline int tiles_x(int W) { return (W + kTileW - 1) / kTileW; }
 inline int tiles_y(int H) { return (H + kTileH - 1) / kTileH; }
 
@@ -103,7 +135,7 @@ struct RasterLaunch {
     int split = 1;        // CTAs per (candidate, tile): 1, 2, 4 or 8
     bool fused = false;   // decode inside the raster (needs the genomes, ceil(N / split) <= kListCap)
     bool small_grid = false;  // at most one wave of CTAs: latency matters more than L1 traffic
-    bool interior_first = false;  // one to a few waves: start the expensive (interior) tiles first
+    bool interior_first = false;  // two CTAs per SM to a few waves: tile-major, tiles from the centre outwards
     const float *d_genomes = nullptr;
     int layout = GGS_LAYOUT_AXES_ANGLE, cols = 9;
     float k_sigma = 3.0f;

@@ -415,11 +415,12 @@ struct TileGeom {
 };
 
 // CTA index -> (candidate, tile).  Candidate-major by default: the tiles of a candidate run
-// together and share its records in L1 / L2.  `interior_first` (grids of one to a few waves, where
-// the LAST wave decides the launch time): tile-major with the image's interior tiles ahead of its
-// border tiles, so that the CTAs that start last are the cheap ones -- a border tile lists about
-// 60 % of the splats of an interior one.  Results do not depend on the order (partials are stored
-// and summed by tile index).
+// together and share its records in L1 / L2.  `interior_first` (grids from two CTAs per SM to a few
+// waves, where the LAST CTAs an SM is dealt decide the launch time): tile-major, the image's tiles
+// from the centre outwards, so that the CTAs that start last -- or that land on the SMs holding
+// one CTA more than the others -- are the cheap ones: a border tile lists about 60 % of the
+// splats of an interior one, a corner tile a third.  Results do not depend on the order (partials
+// are stored and summed by tile index).
 template <bool kInteriorFirst = false>
 __device__ __forceinline__ TileGeom tile_geometry(int cand_tile, int ntx, int ntiles, int lane, int warp,
                                                   int B = 1)
@@ -427,24 +428,10 @@ __device__ __forceinline__ TileGeom tile_geometry(int cand_tile, int ntx, int nt
     TileGeom g;
     int tx, ty;
     if (kInteriorFirst) {
-        const int nty = ntiles / ntx, wi = ntx - 2, n_int = wi * (nty - 2);
+        const int nty = ntiles / ntx;
         const int r = cand_tile / B;
         g.b = cand_tile - r * B;
-        if (r < n_int) {
-            ty = 1 + r / wi;
-            tx = 1 + r - (ty - 1) * wi;
-        } else {
-            int k = r - n_int;  // the border, ring-wise: top row, bottom row, left and right columns
-            if (k < ntx) {
-                ty = 0, tx = k;
-            } else if (k < 2 * ntx) {
-                ty = nty - 1, tx = k - ntx;
-            } else {
-                k -= 2 * ntx;
-                ty = 1 + (k >> 1);
-                tx = (k & 1) ? ntx - 1 : 0;
-            }
-        }
+        centre_out_tile(r, ntx, nty, tx, ty);
     } else {
         g.b = cand_tile / ntiles;
         const int t = cand_tile - g.b * ntiles;
@@ -832,7 +819,7 @@ __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_kernel(const 
 // kDecode: 0 = records from decode_kernel, 1 = fused decode of axes-angle genomes, 2 = fused
 // decode of Cholesky genomes.  blockIdx.x = (candidate * ntiles + tile) * split + k; CTA k owns
 // genome rows [k*S, min(N, (k+1)*S)), S = ceil(N / split); the highest k is the front-most.
-template <int kDecode>
+template <int kDecode, bool kInteriorFirst>
 __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_split_kernel(const __grid_constant__ RasterArgs a)
 {
     unsigned work[2] = {0u, 0u};
@@ -840,7 +827,7 @@ __global__ void __launch_bounds__(kThreads, GGS_MIN_BLOCKS) raster_split_kernel(
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int K = a.split;
     const int k = (int)(blockIdx.x % (unsigned)K);
-    const TileGeom g = tile_geometry((int)(blockIdx.x / (unsigned)K), a.ntx, a.ntiles, lane, warp);
+    const TileGeom g = tile_geometry<kInteriorFirst>((int)(blockIdx.x / (unsigned)K), a.ntx, a.ntiles, lane, warp, a.B);
     const int S = (a.N + K - 1) / K;
     const int i_lo = min(k * S, a.N), n = min(a.N, i_lo + S) - i_lo;
 
@@ -951,15 +938,19 @@ cudaError_t launch_raster(const RasterLaunch &q, cudaStream_t stream)
     a.split = split;
     a.prefetch_inputs = q.small_grid ? 1 : 0;
     a.B = q.B;
-    const bool interior_first = q.interior_first && split == 1 && ntx >= 3 && ntiles / ntx >= 3;
+    const bool interior_first = q.interior_first && ntx >= 3 && ntiles / ntx >= 3;
     a.peers = q.peers;
     if (q.fused) {
         if (!fused_decode_possible(q.N, split)) return cudaErrorInvalidConfiguration;
         if (q.layout == GGS_LAYOUT_AXES_ANGLE)
-            return launch_kernel_cluster(raster_split_kernel<1>, (unsigned)grid, kThreads, 0, split, stream, a);
-        return launch_kernel_cluster(raster_split_kernel<2>, (unsigned)grid, kThreads, 0, split, stream, a);
+            return launch_kernel_cluster(raster_split_kernel<1, false>, (unsigned)grid, kThreads, 0, split, stream, a);
+        return launch_kernel_cluster(raster_split_kernel<2, false>, (unsigned)grid, kThreads, 0, split, stream, a);
     }
-    if (split > 1) return launch_kernel_cluster(raster_split_kernel<0>, (unsigned)grid, kThreads, 0, split, stream, a);
+    if (split > 1) {
+        if (interior_first)
+            return launch_kernel_cluster(raster_split_kernel<0, true>, (unsigned)grid, kThreads, 0, split, stream, a);
+        return launch_kernel_cluster(raster_split_kernel<0, false>, (unsigned)grid, kThreads, 0, split, stream, a);
+    }
     if (q.d_stats != nullptr)
         return launch_kernel(raster_kernel<true, false>, (unsigned)grid, kThreads, 0, stream, a);
     if (interior_first)

@@ -157,8 +157,15 @@ def choose_split(B: int, N: int, H: int, W: int) -> int:
 
 
 def set_option(name: str, value: int) -> None:
-    """Process-wide switch of the library: "pdl", "split", "fuse" (ggs_set_option)."""
+    """Process-wide switch of the library: "pdl", "split", "fuse", "tile_order" (ggs_set_option)."""
     check(lib().ggs_set_option(name.encode(), int(value)), "ggs_set_option")
+
+
+def tile_order(ntx: int, nty: int):
+    """The centre-out order of an ntx x nty tile grid as a list of (tx, ty) (ggs_tile_order; host only)."""
+    out = (ctypes.c_int * (2 * ntx * nty))()
+    check(lib().ggs_tile_order(int(ntx), int(nty), out), "ggs_tile_order")
+    return [(out[2 * r], out[2 * r + 1]) for r in range(ntx * nty)]
 
 
 def probe_peaks() -> dict:

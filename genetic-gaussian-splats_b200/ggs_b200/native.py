@@ -39,6 +39,7 @@ SIGNATURES = {
                             _i, _vp]),
     "ggs_choose_split": (_i, [_i, _i, _i, _i]),
     "ggs_set_option": (_i, [ctypes.c_char_p, _i]),
+    "ggs_tile_order": (_i, [_i, _i, ctypes.POINTER(_i)]),
     "ggs_ctx_create": (_i, [_i, ctypes.POINTER(_vp)]),
     "ggs_ctx_destroy": (None, [_vp]),
     "ggs_ctx_set_target": (_i, [_vp, _vp, _vp, _i, _i]),

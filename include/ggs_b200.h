@@ -145,11 +145,15 @@ int ggs_fitness_ex(const float *d_genomes, int layout, int B, int N, int cols, i
  * between the kernels of a step.  "split" (GGS_B200_SPLIT, default 0 = automatic): force 1, 2, 4
  * or 8 wherever the caller does not pass one.  "fuse" (GGS_B200_FUSE, default 0 = never): 1 = decode
  * inside the raster launch whenever a segment fits the list, -1 = only for single-wave grids.
- * "tile_order" (GGS_B200_TILE_ORDER, default 1): grids of one to four waves launch the image's
- * interior tiles ahead of its border tiles (the last wave is then made of the cheap ones); 0 =
+ * "tile_order" (GGS_B200_TILE_ORDER, default 1): grids between two CTAs per SM and four waves
+ * launch the image's tiles from the centre outwards, tile-major (the CTAs an SM is dealt last are
+ * then the cheap ones: a border tile lists ~60 % of the splats of an interior one); 0 =
  * candidate-major always.  Results are bit-identical either way.
  */
 int ggs_set_option(const char *name, int value);
+/* The centre-out tile order itself, for inspection and tests (host only, no GPU work): writes
+ * (tx, ty) of the tile of rank r to out_xy[2r], out_xy[2r + 1] for r = 0 .. ntx * nty - 1. */
+int ggs_tile_order(int ntx, int nty, int *out_xy);
 
 /* ---- host-buffer path (fitness_population, modules/fitness.py:35-48) ------------- */
 

@@ -175,3 +175,19 @@ def test_run_scripts_can_import_everything_they_need():
                        "k_sigma", "mask_strength", "boost_only", "iterations", "temp0",
                        "temp_schedule", "tries_per_iter", "save_video", "frame_every", "video_dir",
                        "prefix", "loss_png_path", "loss_csv_path", "loss_log_y", "batch_neighbors"]
+
+
+def test_centre_out_tile_order_is_a_permutation_from_the_centre_outwards():
+    """ggs_tile_order (host only): the CTA order of grids between two CTAs per SM and four waves.
+    Every tile exactly once; the distance from the image border never increases along the order;
+    the four image corners come last."""
+    import ggs_b200
+    for ntx in range(1, 34):
+        for nty in (1, 2, 3, 4, 5, 8, 13, 16, 31, 32):
+            order = ggs_b200.tile_order(ntx, nty)
+            assert sorted(order) == [(x, y) for x in range(ntx) for y in range(nty)], (ntx, nty)
+            ring = [min(x, y, ntx - 1 - x, nty - 1 - y) for x, y in order]
+            assert all(a >= b for a, b in zip(ring, ring[1:])), (ntx, nty)
+            if ntx >= 3 and nty >= 3:
+                assert set(order[-4:]) == {(0, 0), (ntx - 1, 0), (0, nty - 1), (ntx - 1, nty - 1)}
+    assert ggs_b200.tile_order(8, 8)[:4] == [(3, 3), (4, 3), (3, 4), (4, 4)]
