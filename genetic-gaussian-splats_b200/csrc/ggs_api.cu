@@ -26,7 +26,7 @@ void set_error(const char *fmt, ...)
 struct Options {
     int pdl;    // programmatic dependent launch between the kernels of a step (GGS_B200_PDL, default 1)
     int split;  // CTAs per (candidate, tile): 0 = automatic (GGS_B200_SPLIT)
-    int tile_order;  // 1 (default): grids between two CTAs per SM and four waves run the tiles centre-out
+    int tile_order;  // 1 (default): grids between two CTAs per SM and sixteen waves run the tiles centre-out
                      // (GGS_B200_TILE_ORDER); 0: candidate-major always.  Results do not depend on it.
     int fuse;   // decode fused into the raster: 0 = never (default), 1 = whenever a segment fits the
                 // list, -1 = when the grid is a single wave and it fits (GGS_B200_FUSE).  Measured on
@@ -228,13 +228,14 @@ int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, 
     const int fuse = stats ? 0 : (opt.fuse >= 0 ? opt.fuse : options().fuse);
     const int64_t ctas = (int64_t)B * tiles_x(W) * tiles_y(H) * q.split;
     q.small_grid = ctas <= wave_slots();
-    // measured (tools/time_cta_order.py): 4-9 % on grids of one to four waves, a loss on deep
+    // measured (tools/time_cta_order.py): 4-11 % on grids of one to four waves, a loss on deep
     // genomes, where saturation and not the list length decides what a tile costs
     // and 8-12 % on grids of LESS than a wave with more than one CTA per SM: the block scheduler
     // deals CTAs to the SMs in index order, so heavy tiles first means the SMs that get one CTA more
     // than the others get a light one (tools/time_cta_order_small.py)
+    // (tools/time_cta_order_large.py: still -4 % at 4.3 waves, -2.5 % at 7, -1 % at 14, nothing at 55)
     q.interior_first = options().tile_order != 0 && N <= 1536 && ctas > wave_slots() / 8 &&
-                       ctas <= 4 * (int64_t)wave_slots();
+                       ctas <= 16 * (int64_t)wave_slots();
     q.fused = !opt.decoded && N > 0 && fuse != 0 && fused_decode_possible(N, q.split) &&
               (fuse == 1 || q.small_grid);
 

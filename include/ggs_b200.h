@@ -145,7 +145,7 @@ int ggs_fitness_ex(const float *d_genomes, int layout, int B, int N, int cols, i
  * between the kernels of a step.  "split" (GGS_B200_SPLIT, default 0 = automatic): force 1, 2, 4
  * or 8 wherever the caller does not pass one.  "fuse" (GGS_B200_FUSE, default 0 = never): 1 = decode
  * inside the raster launch whenever a segment fits the list, -1 = only for single-wave grids.
- * "tile_order" (GGS_B200_TILE_ORDER, default 1): grids between two CTAs per SM and four waves
+ * "tile_order" (GGS_B200_TILE_ORDER, default 1): grids between two CTAs per SM and sixteen waves
  * launch the image's tiles from the centre outwards, tile-major (the CTAs an SM is dealt last are
  * then the cheap ones: a border tile lists ~60 % of the splats of an interior one); 0 =
  * candidate-major always.  Results are bit-identical either way.

@@ -178,7 +178,7 @@ def test_run_scripts_can_import_everything_they_need():
 
 
 def test_centre_out_tile_order_is_a_permutation_from_the_centre_outwards():
-    """ggs_tile_order (host only): the CTA order of grids between two CTAs per SM and four waves.
+    """ggs_tile_order (host only): the CTA order of grids between two CTAs per SM and sixteen waves.
     Every tile exactly once; the distance from the image border never increases along the order;
     the four image corners come last."""
     import ggs_b200

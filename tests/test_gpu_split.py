@@ -129,15 +129,16 @@ def test_automatic_split_policy(ggs):
 
 
 def test_cta_order_does_not_change_a_bit(ggs):
-    """Grids of more than one CTA per SM and at most four waves run tile-major, interior tiles first
+    """Grids of more than one CTA per SM and at most sixteen waves run tile-major, tiles centre-out
     (the split kernel too); partial sums are stored and added by tile index, so images and fitness
-    are those of the candidate-major order.  Shapes: 1-4 waves, less than a wave (BASELINE configs
+    are those of the candidate-major order.  Shapes: 1-14 waves, less than a wave (BASELINE configs
     1 and 2), cluster splits 2 / 4 / 8, ragged image sizes."""
     from ggs_b200 import synth
     for (B, N, H, W, split) in ((30, 300, 256, 256, 0), (24, 512, 256, 256, 0), (70, 90, 200, 136, 0),
                                 (5, 400, 512, 512, 0), (32, 100, 128, 128, 0), (8, 500, 256, 256, 0),
                                 (3, 500, 256, 256, 0), (1, 500, 256, 256, 8), (2, 300, 200, 136, 4),
-                                (6, 200, 256, 256, 2), (16, 100, 128, 128, 0)):
+                                (6, 200, 256, 256, 2), (16, 100, 128, 128, 0), (130, 120, 256, 256, 0),
+                                (260, 60, 256, 256, 0)):
         g = cuda(synth.new_population_np(B, N, H, W, seed=B))
         t = cuda(synth.synthetic_target_np(H, W, B))
         m = cuda(np.random.default_rng(B).uniform(0.2, 1.0, size=(H, W)).astype(np.float32))
