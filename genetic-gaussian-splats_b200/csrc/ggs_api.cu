@@ -228,12 +228,13 @@ int evaluate(const float *d_genomes, int layout, int B, int N, int cols, int H, 
     const int fuse = stats ? 0 : (opt.fuse >= 0 ? opt.fuse : options().fuse);
     const int64_t ctas = (int64_t)B * tiles_x(W) * tiles_y(H) * q.split;
     q.small_grid = ctas <= wave_slots();
-    // measured (tools/time_cta_order.py): 4-11 % on grids of one to four waves, a loss on deep
-    // genomes, where saturation and not the list length decides what a tile costs
-    // and 8-12 % on grids of LESS than a wave with more than one CTA per SM: the block scheduler
-    // deals CTAs to the SMs in index order, so heavy tiles first means the SMs that get one CTA more
-    // than the others get a light one (tools/time_cta_order_small.py)
-    // (tools/time_cta_order_large.py: still -4 % at 4.3 waves, -2.5 % at 7, -1 % at 14, nothing at 55)
+    // Centre-out CTA order (ggs_raster.cu, tile_geometry).  Measured: -4..-11 % on grids of one to
+    // four waves (tools/time_cta_order.py), -8..-15 % on grids of LESS than a wave with more than one
+    // CTA per SM -- the block scheduler deals CTAs to the SMs in index order, so with the heavy
+    // tiles first the SMs that get one CTA more than the others get a light one
+    // (tools/time_cta_order_small.py) -- still -4 % at 4.3 waves, -2.5 % at 7, -1 % at 14, nothing at
+    // config 3's 55 (tools/time_cta_order_large.py); nothing on deep genomes, where saturation and
+    // not the list length decides what a tile costs.
     q.interior_first = options().tile_order != 0 && N <= 1536 && ctas > wave_slots() / 8 &&
                        ctas <= 16 * (int64_t)wave_slots();
     q.fused = !opt.decoded && N > 0 && fuse != 0 && fused_decode_possible(N, q.split) &&
