@@ -66,17 +66,22 @@ int choose_split(int B, int N, int H, int W)
 {
     const int forced = options().split;
     if (forced == 1 || forced == 2 || forced == 4 || forced == 8) return forced;
-    // Measured on the B200 (profiles/r02_small_batch.txt): the split pays while the grid leaves
-    // most SMs with less than one CTA per scheduler -- B * tiles * split within HALF a wave --
-    // (one SA try at 256x256: 25.7 -> 13.8 us at split 8) and stops paying at 512 CTAs (configs 1
-    // and 2: split 1 is the fastest); and it must not be used on deep genomes, whose bands go
-    // opaque early: the segments cannot see each other's saturation (512x512 / 4,000 splats, one
-    // frame: 40.8 us at split 1, 68 us at split 4).
+    // Measured on the B200 (tools/time_split_policy.py, profiles/r02_split_policy.txt): a cluster of 8
+    // pays only while the grid stays within HALF a wave (one SA try at 256x256: 26.0 -> 13.8 us; two
+    // candidates: 17.4 us at 8 against 15.9 at 4 -- every CTA folds `split` states); 2 and 4 pay up to
+    // ~7 CTAs per SM (1,024 CTAs on 148 SMs) as long as the unsplit grid has less than 3 CTAs per SM
+    // (3 candidates at 256x256: 20.9 us at 2, 18.1 at 4; 8 candidates = 512 CTAs: split 1 is the
+    // fastest); segments keep at least 16 splats; and never on deep genomes, whose bands go opaque
+    // early: the segments cannot see each other's saturation (512x512 / 4,000 splats, one frame:
+    // 40.8 us at split 1, 68 us at split 4).
     if (N > 1536) return 1;
     const int64_t ctas = (int64_t)B * tiles_x(W) * tiles_y(H);
-    const int slots = wave_slots() / 2;
+    const int slots = wave_slots();
+    const auto segment_ok = [N](int k) { return (N + k - 1) / k >= 16; };
+    if (ctas * 8 <= slots / 2 && segment_ok(8)) return 8;
     int k = 1;
-    while (k < kMaxSplit && ctas * (k * 2) <= slots && (N + 2 * k - 1) / (2 * k) >= 16) k *= 2;
+    if (ctas * 8 < slots * 3)  // fewer than 3 CTAs per SM unsplit
+        while (k < 4 && ctas * (k * 2) <= slots - slots / 8 && segment_ok(2 * k)) k *= 2;
     return k;
 }
 

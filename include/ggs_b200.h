@@ -126,8 +126,9 @@ int ggs_fitness(const float *d_genomes, int layout, int B, int N, int cols, int 
  * the k-th segment of the genome and the partial (colour, transmittance) states are folded in
  * genome order through distributed shared memory ("over" is associative).  (A variant that also
  * fuses the decode into that launch exists behind the "fuse" option; it measured slower and is off.)
- * Every entry point picks `split` from B (ggs_choose_split: the largest split that keeps the grid
- * within half a wave -- 4 CTAs per SM -- and 1 for genomes of more than 1,536 splats, whose
+ * Every entry point picks `split` from B (ggs_choose_split, from measurements: 8 while the grid
+ * stays within half a wave, else 2 or 4 up to about 7 CTAs per SM while the unsplit grid has
+ * fewer than 3 per SM, segments of at least 16 splats, and 1 for genomes of more than 1,536 splats, whose
  * segments would lose the saturation stop).  The fold changes the floating-point association, so results for different
  * `split` agree to ~1e-7 but not bit for bit: a caller that evaluates ONE population in several
  * calls or on several GPUs and wants the bits of a single call passes the split of the whole

@@ -96,21 +96,27 @@ def test_a_given_split_is_deterministic_and_independent_of_the_call_boundaries(g
 
 
 def test_automatic_split_policy(ggs):
-    # half a wave (4 CTAs per SM); segments of at least 16 splats; never on deep genomes
+    # 8 within half a wave; 2 / 4 up to 7 CTAs per SM while the unsplit grid has fewer than 3 per SM;
+    # segments of at least 16 splats; never on deep genomes
     import ggs_b200
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    slots = 4 * sms
+    slots = 8 * sms
     assert ggs.choose_split(1024, 1000, 256, 256) == 1          # config 3: throughput path
     assert ggs.choose_split(1, 500, 256, 256) == 8              # one SA try: 64 tiles x 8
+    assert ggs.choose_split(2, 500, 256, 256) == 4              # 8 would be 1,024 CTAs folding 8 states each
+    assert ggs.choose_split(3, 500, 256, 256) == 4              # 768 CTAs
+    assert ggs.choose_split(6, 500, 256, 256) == 2              # 768 CTAs
     assert ggs.choose_split(32, 100, 128, 128) == 1             # config 1: 512 CTAs already
     assert ggs.choose_split(8, 500, 256, 256) == 1              # config 2, 8 neighbours: likewise
     assert ggs.choose_split(1, 4000, 512, 512) == 1             # deep genome: keep the saturation stop
-    for B, N, side in ((32, 100, 128), (8, 500, 256), (4, 20, 64), (3, 1000, 512), (2, 500, 256)):
+    for B, N, side in ((32, 100, 128), (8, 500, 256), (4, 20, 64), (3, 1000, 512), (2, 500, 256), (12, 100, 128),
+                       (1, 1000, 512), (5, 64, 96)):
         tiles = ((side + 31) // 32) ** 2
         k = ggs.choose_split(B, N, side, side)
-        assert k in (1, 2, 4, 8) and B * tiles * k <= max(slots, B * tiles)
+        assert k in (1, 2, 4, 8)
         assert k == 1 or -(-N // k) >= 16
-        assert k == 8 or B * tiles * 2 * k > slots or -(-N // (2 * k)) < 16
+        assert k == 1 or B * tiles * k <= slots - slots // 8
+        assert k != 8 or B * tiles * 8 <= slots // 2
     # the default entry uses it: same bits as the explicit call
     from ggs_b200 import synth
     g = cuda(synth.new_population_np(4, 300, 128, 128, seed=9))
